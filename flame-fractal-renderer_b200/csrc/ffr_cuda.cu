@@ -1,0 +1,1056 @@
+/*
+ffr_cuda.cu -- C ABI of libffr_cuda (include/ffr_cuda.h): context, flame blob packing,
+kernel dispatch, multi-GPU sharding and peer-memory reduce. No CPU fallback: every entry
+point that computes needs an sm_100 device and fails loudly without one.
+*/
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ffr_kernels.cuh"
+
+#define FFR_VERSION_STRING "ffr-b200 0.1 (sm_100a, double/u64)"
+
+namespace
+{
+
+/* polar quantities each 2-d variation reads (see calc2d in ffr_device.cuh) */
+uint32_t op_need(uint32_t op)
+{
+    const uint32_t R2 = NEED_R2, R = NEED_R2|NEED_R, A = NEED_ANG, SC = NEED_R2|NEED_R|NEED_SC;
+    switch (op)
+    {
+    case FFR_VAR_SWIRL: return R2;
+    case FFR_VAR_HORSESHOE: return R;
+    case FFR_VAR_POLAR: return A|R;
+    case FFR_VAR_POLAR2: return A|R2;
+    case FFR_VAR_HANDKERCHIEF: return A|R;
+    case FFR_VAR_HEART: return A|R;
+    case FFR_VAR_DISC: return A|R;
+    case FFR_VAR_DISC2: return A;
+    case FFR_VAR_FAN: return A|R;
+    case FFR_VAR_RINGS: return SC;
+    case FFR_VAR_SPIRAL: return SC;
+    case FFR_VAR_HYPERBOLIC: return SC;
+    case FFR_VAR_DIAMOND: return SC;
+    case FFR_VAR_EX: return A|R;
+    case FFR_VAR_JULIA: return A|R;
+    case FFR_VAR_POWER: return SC;
+    case FFR_VAR_BLOB: return SC|A;
+    case FFR_VAR_JULIAN: return A|R2;
+    case FFR_VAR_JULIASCOPE: return A|R2;
+    case FFR_VAR_RADIAL_BLUR: return A|R;
+    case FFR_VAR_NGON: return A|R2;
+    case FFR_VAR_RAYS: return R2;
+    case FFR_VAR_BLADE: return R;
+    case FFR_VAR_SECANT: return R;
+    case FFR_VAR_TWINTRIAN: return R;
+    case FFR_VAR_LOG: return A|R2;
+    case FFR_VAR_SCRY: return R;
+    case FFR_VAR_WEDGE: return A|R;
+    case FFR_VAR_WEDGE_JULIA: return A|R2;
+    case FFR_VAR_WEDGE_SPH: return A|R;
+    case FFR_VAR_WHORL: return A|R;
+    case FFR_VAR_SUPERSHAPE: return A|R;
+    case FFR_VAR_FLOWER: return A|R;
+    case FFR_VAR_CONIC: return R;
+    case FFR_VAR_PARABOLA: return R;
+    case FFR_VAR_BIPOLAR: return R2;
+    case FFR_VAR_CPOW: return A|R2;
+    case FFR_VAR_EDISC: return R2;
+    case FFR_VAR_ELLIPTIC: return R2;
+    case FFR_VAR_ESCHER: return A|R2;
+    case FFR_VAR_LOONIE: return R2;
+    default: return 0;
+    }
+}
+
+bool op_uses_rng(uint32_t op)
+{
+    switch (op)
+    {
+    case FFR_VAR_NOISE: case FFR_VAR_BLUR: case FFR_VAR_GAUSSIAN_BLUR: case FFR_VAR_SQUARE_NOISE:
+    case FFR_VAR_PRE_BLUR: case FFR_VAR_JULIA: case FFR_VAR_JULIAN: case FFR_VAR_JULIASCOPE:
+    case FFR_VAR_RADIAL_BLUR: case FFR_VAR_PIE: case FFR_VAR_ARCH: case FFR_VAR_RAYS:
+    case FFR_VAR_BLADE: case FFR_VAR_TWINTRIAN: case FFR_VAR_WEDGE_JULIA: case FFR_VAR_SUPERSHAPE:
+    case FFR_VAR_FLOWER: case FFR_VAR_CONIC: case FFR_VAR_PARABOLA: case FFR_VAR_BOARDERS:
+    case FFR_VAR_CPOW:
+        return true;
+    default:
+        return false;
+    }
+}
+
+/* seed-independent randmem: Isaac<u64,4>::init(flag=false), isaac.hpp:102-117 */
+void isaac_m0(u64 m[16])
+{
+    u64 a,b,c,d,e,f,g,h;
+    a = b = c = d = e = f = g = h = 0x9e3779b97f4a7c13ULL;
+#define MIX() do { \
+    a -= e; f ^= h >>  9; h += a; \
+    b -= f; g ^= a <<  9; a += b; \
+    c -= g; h ^= b >> 23; b += c; \
+    d -= h; a ^= c << 15; c += d; \
+    e -= a; b ^= d >> 14; d += e; \
+    f -= b; c ^= e << 20; e += f; \
+    g -= c; d ^= f >> 17; f += g; \
+    h -= d; e ^= g << 14; g += h; } while (0)
+    MIX(); MIX(); MIX(); MIX();
+    for (int i = 0; i < 16; i += 8)
+    {
+        MIX();
+        m[i+0] = a; m[i+1] = b; m[i+2] = c; m[i+3] = d;
+        m[i+4] = e; m[i+5] = f; m[i+6] = g; m[i+7] = h;
+    }
+#undef MIX
+}
+
+struct DeviceState
+{
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    u64 *buffer = nullptr;
+    bool own_buffer = false;
+    DevFlame *d_blob = nullptr;
+    double *d_colors = nullptr;
+    DevStats *d_stats = nullptr;
+    unsigned int *d_counter = nullptr;
+    u64 *d_scratch = nullptr;      /* 2 x u64 for histogram sum/max */
+    int sm_count = 0;
+    int blocks_per_sm = 0;
+    bool dirty = false;            /* holds samples not yet reduced into device 0 */
+};
+
+typedef void (*render_fn)(const RenderParams);
+
+} // namespace
+
+struct ffr_ctx
+{
+    uint32_t dims = 0, r = 0, cellsz = 1;
+    u64 cells = 0;
+    size_t bytes = 0;
+    uint32_t num_xforms = 0, num_ids = 0;
+    bool has_final = false, affine_only = false;
+    std::vector<unsigned char> blob;
+    std::vector<double> colors;
+    std::vector<u64> json_ids;     /* sorted index -> JSON id */
+    std::vector<DeviceState> devs;
+    ffr_options opt;
+    uint32_t scatter_mode = FFR_SCATTER_GLOBAL;
+    render_fn kernel = nullptr;
+    size_t smem_bytes = 0;
+    u64 launches = 0;
+    std::string err;
+    bool peer_enabled = false;
+};
+
+namespace
+{
+
+thread_local std::string g_create_err;
+
+bool cuda_ok(ffr_ctx *ctx, cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess)
+        return true;
+    std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+    if (ctx)
+        ctx->err = msg;
+    else
+        g_create_err = msg;
+    return false;
+}
+
+#define CK(call) do { if (!cuda_ok(ctx,(call),#call)) return FFR_E_CUDA; } while (0)
+
+template <int D, int RCAP>
+render_fn pick_affine(bool affine_only)
+{
+    return affine_only ? (render_fn)render_kernel<D,RCAP,true> : (render_fn)render_kernel<D,RCAP,false>;
+}
+
+template <int D>
+render_fn pick_rcap(uint32_t r, bool affine_only)
+{
+    if (r == 0) return pick_affine<D,0>(affine_only);
+    if (r <= 4) return pick_affine<D,4>(affine_only);
+    return pick_affine<D,FFR_MAX_COLOR_DIMS>(affine_only);
+}
+
+render_fn pick_kernel(uint32_t dims, uint32_t r, bool affine_only)
+{
+    switch (dims)
+    {
+    case 1: return pick_rcap<1>(r,affine_only);
+    case 2: return pick_rcap<2>(r,affine_only);
+    case 3: return pick_rcap<3>(r,affine_only);
+    default: return nullptr;
+    }
+}
+
+/* flatten the caller's desc into the device blob (DevFlame | DevXForm[] | DevVar[]) */
+bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
+{
+    if (!d || d->dims < 1 || d->dims > FFR_MAX_DIMS)
+    {
+        err = "dimensions not supported";
+        return false;
+    }
+    if (d->elem_size != 8)
+    {
+        err = "only the double/u64 build (elem_size 8) is implemented";
+        return false;
+    }
+    if (d->color_dims > FFR_MAX_COLOR_DIMS)
+    {
+        err = "too many color dimensions";
+        return false;
+    }
+    if (d->num_xforms == 0 || !d->xforms || !d->xfcw)
+    {
+        err = "Flame(): no xforms";
+        return false;
+    }
+    if (d->num_xforms > FFR_MAX_XFORMS || d->num_xform_ids > FFR_MAX_XFORMS)
+    {
+        err = "libffr_cuda supports at most 64 xforms";
+        return false;
+    }
+    DevFlame hdr;
+    memset(&hdr,0,sizeof(hdr));
+    hdr.dims = d->dims;
+    hdr.r = d->color_dims;
+    hdr.has_final = d->has_final && d->final_xform;
+    hdr.num_xforms = d->num_xforms;
+    hdr.num_ids = d->num_xform_ids;
+    /* BufferRenderer::_init, buffer_renderer.hpp:114-140 */
+    const double scale_adjust_down = 1.0 - (double)(float)(1.0 / (double)(1L << 52));
+    u64 cells = 1;
+    for (uint32_t i = 0; i < d->dims; ++i)
+    {
+        if (d->size[i] == 0 || !(d->bounds_lo[i] < d->bounds_hi[i]))
+        {
+            err = "Flame(): bad size or bounds";
+            return false;
+        }
+        hdr.lo[i] = d->bounds_lo[i];
+        hdr.hi[i] = d->bounds_hi[i];
+        hdr.mult_d[i] = (double)(d->size[i]) / (d->bounds_hi[i] - d->bounds_lo[i]);
+        hdr.mult_d[i] *= scale_adjust_down;
+        hdr.mult_i[i] = cells;
+        cells *= d->size[i];
+        if (cells >= (1ULL << 48))
+        {
+            err = "BufferRenderer(): histogram too big";
+            return false;
+        }
+    }
+    hdr.cells = cells;
+    hdr.cell = 1 + d->color_dims;
+    for (uint32_t i = 0; i < d->num_xforms; ++i)
+        hdr.xfcw[i] = d->xfcw[i];
+
+    std::vector<DevXForm> xfs;
+    std::vector<DevVar> vars;
+    ctx->colors.clear();
+    ctx->json_ids.clear();
+    bool affine_only = true, uses_rng = false;
+    const uint32_t total = d->num_xforms + (hdr.has_final ? 1 : 0);
+    for (uint32_t i = 0; i < total; ++i)
+    {
+        const ffr_xform &x = (i < d->num_xforms) ? d->xforms[i] : *d->final_xform;
+        DevXForm dx;
+        memset(&dx,0,sizeof(dx));
+        memcpy(dx.pre_A,x.pre_A,sizeof(dx.pre_A));
+        memcpy(dx.pre_b,x.pre_b,sizeof(dx.pre_b));
+        memcpy(dx.post_A,x.post_A,sizeof(dx.post_A));
+        memcpy(dx.post_b,x.post_b,sizeof(dx.post_b));
+        dx.color_speed = x.color_speed;
+        dx.var_begin = (uint32_t)vars.size();
+        dx.var_count = x.num_vars;
+        dx.flags = (x.has_pre ? XF_HAS_PRE : 0) | (x.has_post ? XF_HAS_POST : 0);
+        if (i < d->num_xforms)
+        {
+            if (x.id >= FFR_MAX_XFORMS)
+            {
+                err = "xform id out of range";
+                return false;
+            }
+            ctx->json_ids.push_back(x.id);
+            dx.json_id = (uint32_t)x.id;
+        }
+        else
+            dx.json_id = 0xffffffffu;
+        if (x.has_color && x.color && d->color_dims)
+        {
+            dx.flags |= XF_HAS_COLOR;
+            dx.color_off = (uint32_t)ctx->colors.size();
+            for (uint32_t k = 0; k < d->color_dims; ++k)
+                ctx->colors.push_back(x.color[k]);
+        }
+        for (uint32_t k = 0; k < x.num_vars; ++k)
+        {
+            const ffr_variation &v = x.vars[k];
+            if (v.op < 1 || v.op > FFR_VAR_COUNT)
+            {
+                err = "unknown variation opcode";
+                return false;
+            }
+            const bool v2d = v.op >= FFR_VAR_FIRST_2D && v.op <= FFR_VAR_LAST_2D;
+            if (v2d && d->dims < 2)
+            {
+                err = "2-d variation in a 1-d flame";
+                return false;
+            }
+            if (v2d && d->dims > 2 && (v.axis_x >= d->dims || v.axis_y >= d->dims || v.axis_x == v.axis_y))
+            {
+                err = "axis index out of range";
+                return false;
+            }
+            DevVar dv;
+            memset(&dv,0,sizeof(dv));
+            dv.op = v.op;
+            dv.axis_x = (d->dims == 2) ? 0 : v.axis_x;
+            dv.axis_y = (d->dims == 2) ? 1 : v.axis_y;
+            dv.need = op_need(v.op);
+            dv.weight = v.weight;
+            memcpy(dv.p,v.params,sizeof(dv.p));
+            dx.need |= dv.need;
+            if (v.op != FFR_VAR_LINEAR)
+                affine_only = false;
+            if (op_uses_rng(v.op))
+            {
+                dx.flags |= XF_USES_RNG;
+                uses_rng = true;
+            }
+            vars.push_back(dv);
+        }
+        xfs.push_back(dx);
+    }
+    if (ctx->colors.empty())
+        ctx->colors.push_back(0.0);
+    hdr.num_vars = (uint32_t)vars.size();
+    hdr.uses_rng = uses_rng;
+    hdr.xf_off = (uint32_t)sizeof(DevFlame);
+    hdr.var_off = hdr.xf_off + (uint32_t)(xfs.size()*sizeof(DevXForm));
+    hdr.total_bytes = hdr.var_off + (uint32_t)(vars.size()*sizeof(DevVar));
+    hdr.total_bytes = (hdr.total_bytes + 15u) & ~15u;
+    if (hdr.total_bytes > 96*1024)
+    {
+        err = "flame too large for the shared-memory blob";
+        return false;
+    }
+    ctx->blob.assign(hdr.total_bytes,0);
+    memcpy(ctx->blob.data(),&hdr,sizeof(hdr));
+    memcpy(ctx->blob.data()+hdr.xf_off,xfs.data(),xfs.size()*sizeof(DevXForm));
+    if (!vars.empty())
+        memcpy(ctx->blob.data()+hdr.var_off,vars.data(),vars.size()*sizeof(DevVar));
+    ctx->dims = d->dims;
+    ctx->r = d->color_dims;
+    ctx->cellsz = hdr.cell;
+    ctx->cells = cells;
+    ctx->bytes = (size_t)cells*hdr.cell*8;
+    ctx->num_xforms = d->num_xforms;
+    ctx->num_ids = d->num_xform_ids;
+    ctx->has_final = hdr.has_final;
+    ctx->affine_only = affine_only;
+    return true;
+}
+
+void init_stats_host(DevStats &s)
+{
+    memset(&s,0,sizeof(s));
+    for (int i = 0; i < 3; ++i)
+    {
+        s.pt_min[i] = f64_to_ordered(INFINITY);
+        s.pt_max[i] = f64_to_ordered(-INFINITY);
+    }
+}
+
+int setup_device(ffr_ctx *ctx, DeviceState &ds, int dev, const ffr_options &opt)
+{
+    ds.dev = dev;
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop,dev));
+    if (prop.major < 10)
+    {
+        ctx->err = "device " + std::to_string(dev) + " (" + prop.name + ") is not sm_100 or newer; "
+            "libffr_cuda has no fallback path";
+        return FFR_E_NODEVICE;
+    }
+    ds.sm_count = prop.multiProcessorCount;
+    if (opt.stream)
+        ds.stream = (cudaStream_t)opt.stream;
+    else
+    {
+        CK(cudaStreamCreateWithFlags(&ds.stream,cudaStreamNonBlocking));
+        ds.own_stream = true;
+    }
+    if (opt.external_buffer)
+        ds.buffer = (u64*)opt.external_buffer;
+    else
+    {
+        CK(cudaMalloc(&ds.buffer,ctx->bytes));
+        ds.own_buffer = true;
+        CK(cudaMemsetAsync(ds.buffer,0,ctx->bytes,ds.stream));
+    }
+    CK(cudaMalloc(&ds.d_blob,ctx->blob.size()));
+    CK(cudaMemcpyAsync(ds.d_blob,ctx->blob.data(),ctx->blob.size(),cudaMemcpyHostToDevice,ds.stream));
+    CK(cudaMalloc(&ds.d_colors,ctx->colors.size()*sizeof(double)));
+    CK(cudaMemcpyAsync(ds.d_colors,ctx->colors.data(),ctx->colors.size()*sizeof(double),
+        cudaMemcpyHostToDevice,ds.stream));
+    CK(cudaMalloc(&ds.d_stats,sizeof(DevStats)));
+    DevStats init;
+    init_stats_host(init);
+    CK(cudaMemcpyAsync(ds.d_stats,&init,sizeof(init),cudaMemcpyHostToDevice,ds.stream));
+    CK(cudaMalloc(&ds.d_counter,sizeof(unsigned int)));
+    CK(cudaMalloc(&ds.d_scratch,2*sizeof(u64)));
+    u64 m0[16];
+    isaac_m0(m0);
+    CK(cudaMemcpyToSymbolAsync(c_isaac_m0,m0,sizeof(m0),0,cudaMemcpyHostToDevice,ds.stream));
+    CK(cudaFuncSetAttribute((const void*)ctx->kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,
+        (int)ctx->smem_bytes));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb,(const void*)ctx->kernel,FFR_TPB,ctx->smem_bytes));
+    if (nb < 1)
+    {
+        ctx->err = "render kernel does not fit on the device";
+        return FFR_E_CUDA;
+    }
+    if (opt.blocks_per_sm && (int)opt.blocks_per_sm < nb)
+        nb = (int)opt.blocks_per_sm;
+    ds.blocks_per_sm = nb;
+    CK(cudaStreamSynchronize(ds.stream));
+    return FFR_OK;
+}
+
+int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_count, u64 chain_len,
+        u64 last_len, u64 base_seed, u64 bv_limit)
+{
+    if (chain_count == 0)
+        return FFR_OK;
+    CK(cudaSetDevice(ds.dev));
+    RenderParams prm;
+    prm.blob = ds.d_blob;
+    prm.colors = ds.d_colors;
+    prm.buffer = ds.buffer;
+    prm.stats = ds.d_stats;
+    prm.work_counter = ds.d_counter;
+    prm.chain_first = chain_first;
+    prm.chain_count = chain_count;
+    prm.chain_len = chain_len;
+    prm.last_len = last_len;
+    prm.base_seed = base_seed;
+    prm.bv_limit = bv_limit;
+    prm.blob_bytes = (uint32_t)ctx->blob.size();
+    prm.scatter_mode = ctx->scatter_mode;
+    const u64 groups = (chain_count + FFR_TPB - 1) / FFR_TPB;
+    if (groups > 0xfffffff0ULL)
+    {
+        ctx->err = "too many chains in one launch";
+        return FFR_E_INVALID;
+    }
+    u64 grid = (u64)ds.sm_count * ds.blocks_per_sm;
+    if (grid > groups)
+        grid = groups;
+    CK(cudaMemsetAsync(ds.d_counter,0,sizeof(unsigned int),ds.stream));
+    ctx->kernel<<<(unsigned)grid,FFR_TPB,ctx->smem_bytes,ds.stream>>>(prm);
+    CK(cudaGetLastError());
+    ++ctx->launches;
+    ds.dirty = true;
+    return FFR_OK;
+}
+
+/* reset the per-call bad value list (render() clears it, buffer_renderer.hpp:277-278) */
+int reset_bad(ffr_ctx *ctx, DeviceState &ds)
+{
+    CK(cudaSetDevice(ds.dev));
+    CK(cudaMemsetAsync(&ds.d_stats->n_bad,0,sizeof(u64) + 2*sizeof(uint32_t),ds.stream));
+    return FFR_OK;
+}
+
+int collect_stats(ffr_ctx *ctx, ffr_stats *out)
+{
+    memset(out,0,sizeof(*out));
+    for (int i = 0; i < 3; ++i)
+    {
+        out->pt_min[i] = INFINITY;
+        out->pt_max[i] = -INFINITY;
+    }
+    std::vector<DevStats> hs(1);
+    for (DeviceState &ds : ctx->devs)
+    {
+        CK(cudaSetDevice(ds.dev));
+        CK(cudaMemcpyAsync(&hs[0],ds.d_stats,sizeof(DevStats),cudaMemcpyDeviceToHost,ds.stream));
+        CK(cudaStreamSynchronize(ds.stream));
+        const DevStats &s = hs[0];
+        out->s_iter += s.s_iter;
+        out->s_plot += s.s_plot;
+        for (uint32_t i = 0; i < ctx->num_xforms; ++i)
+            out->xf_dist[ctx->json_ids[i]] += s.xf_dist[i];
+        for (uint32_t i = 0; i < ctx->dims; ++i)
+        {
+            out->pt_min[i] = std::min(out->pt_min[i],ordered_to_f64(s.pt_min[i]));
+            out->pt_max[i] = std::max(out->pt_max[i],ordered_to_f64(s.pt_max[i]));
+        }
+        const u64 nb = std::min<u64>(s.n_bad,FFR_MAX_BAD_RECORDED);
+        for (u64 k = 0; k < nb; ++k)
+        {
+            if (out->n_bad + k < FFR_MAX_BAD_RECORDED)
+            {
+                out->bad_xf[out->n_bad + k] = s.bad_xf[k];
+                for (int d = 0; d < 3; ++d)
+                    out->bad_pt[out->n_bad + k][d] = s.bad_pt[k][d];
+            }
+        }
+        out->n_bad += s.n_bad;
+    }
+    return FFR_OK;
+}
+
+int sync_all(ffr_ctx *ctx)
+{
+    for (DeviceState &ds : ctx->devs)
+    {
+        CK(cudaSetDevice(ds.dev));
+        CK(cudaStreamSynchronize(ds.stream));
+    }
+    return FFR_OK;
+}
+
+bool aborted(ffr_ctx *ctx, u64 bv_limit, const ffr_stats &st)
+{
+    (void)ctx;
+    return st.n_bad > bv_limit;
+}
+
+} // namespace
+
+extern "C"
+{
+
+const char *ffr_cuda_version(void)
+{
+    return FFR_VERSION_STRING;
+}
+
+int ffr_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+uint64_t ffr_chain_seed(uint64_t base_seed, uint64_t chain_index)
+{
+    return splitmix64(base_seed + chain_index);
+}
+
+ffr_ctx *ffr_cuda_create(const ffr_flame_desc *desc, const int *devices, int ndev, char *err,
+        size_t errlen)
+{
+    return ffr_cuda_create_ex(desc,devices,ndev,nullptr,err,errlen);
+}
+
+ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int ndev,
+        const ffr_options *opt, char *err, size_t errlen)
+{
+    ffr_ctx *ctx = new ffr_ctx;
+    std::string msg;
+    auto fail = [&](const std::string& m) -> ffr_ctx*
+    {
+        if (err && errlen)
+            snprintf(err,errlen,"%s",m.c_str());
+        ffr_cuda_destroy(ctx);
+        return nullptr;
+    };
+    memset(&ctx->opt,0,sizeof(ctx->opt));
+    if (opt)
+        memcpy(&ctx->opt,opt,std::min<size_t>(opt->struct_size ? opt->struct_size : sizeof(ffr_options),
+            sizeof(ffr_options)));
+    if (!pack_blob(ctx,desc,msg))
+        return fail(msg);
+    if (ndev < 1)
+        return fail("ffr_cuda_create(): need at least one device");
+    if ((ctx->opt.external_buffer || ctx->opt.stream) && ndev != 1)
+        return fail("ffr_cuda_create(): external buffer / stream need a single device context");
+    int avail = ffr_cuda_device_count();
+    if (avail < 1)
+        return fail("ffr_cuda_create(): no CUDA device available; libffr_cuda has no CPU fallback");
+    ctx->scatter_mode = ctx->opt.scatter_mode;
+    if (ctx->scatter_mode == FFR_SCATTER_AUTO || ctx->scatter_mode == FFR_SCATTER_SMEM_TILE)
+        ctx->scatter_mode = FFR_SCATTER_GLOBAL;
+    ctx->kernel = pick_kernel(ctx->dims,ctx->r,ctx->affine_only);
+    ctx->smem_bytes = FFR_SMEM_RNG_BYTES + ctx->blob.size();
+    ctx->devs.resize(ndev);
+    for (int i = 0; i < ndev; ++i)
+    {
+        int dev = devices ? devices[i] : i;
+        if (dev < 0 || dev >= avail)
+            return fail("ffr_cuda_create(): device index out of range");
+        int rc = setup_device(ctx,ctx->devs[i],dev,ctx->opt);
+        if (rc != FFR_OK)
+            return fail(ctx->err);
+    }
+    return ctx;
+}
+
+void ffr_cuda_destroy(ffr_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    for (DeviceState &ds : ctx->devs)
+    {
+        if (ds.dev < 0)
+            continue;
+        cudaSetDevice(ds.dev);
+        if (ds.stream)
+            cudaStreamSynchronize(ds.stream);
+        if (ds.own_buffer && ds.buffer) cudaFree(ds.buffer);
+        if (ds.d_blob) cudaFree(ds.d_blob);
+        if (ds.d_colors) cudaFree(ds.d_colors);
+        if (ds.d_stats) cudaFree(ds.d_stats);
+        if (ds.d_counter) cudaFree(ds.d_counter);
+        if (ds.d_scratch) cudaFree(ds.d_scratch);
+        if (ds.own_stream && ds.stream) cudaStreamDestroy(ds.stream);
+    }
+    delete ctx;
+}
+
+const char *ffr_cuda_last_error(const ffr_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+size_t ffr_cuda_buffer_bytes(const ffr_ctx *ctx)
+{
+    return ctx ? ctx->bytes : 0;
+}
+
+uint64_t ffr_cuda_buffer_cells(const ffr_ctx *ctx)
+{
+    return ctx ? ctx->cells : 0;
+}
+
+void *ffr_cuda_device_buffer(ffr_ctx *ctx, int dev_index)
+{
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size())
+        return nullptr;
+    return ctx->devs[dev_index].buffer;
+}
+
+int ffr_cuda_add_buffer(ffr_ctx *ctx, const void *host, size_t bytes)
+{
+    if (!ctx || !host)
+        return FFR_E_INVALID;
+    if (bytes != ctx->bytes)
+    {
+        ctx->err = "BufferRenderer::addBuffer(): sizes do not match";
+        return FFR_E_INVALID;
+    }
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    /* stage in chunks so a 1 GiB -i file does not double the footprint */
+    const size_t chunk_elems = (size_t)1 << 24; /* 128 MiB, multiple of any cell size handled below */
+    const size_t n_elems = bytes/8;
+    size_t chunk = std::min(n_elems,chunk_elems - (chunk_elems % ctx->cellsz));
+    u64 *tmp = nullptr;
+    CK(cudaMalloc(&tmp,chunk*8));
+    int rc = FFR_OK;
+    for (size_t off = 0; off < n_elems && rc == FFR_OK; off += chunk)
+    {
+        size_t n = std::min(chunk,n_elems - off);
+        if (!cuda_ok(ctx,cudaMemcpyAsync(tmp,(const u64*)host + off,n*8,cudaMemcpyHostToDevice,ds.stream),
+                "cudaMemcpyAsync(add_buffer)"))
+        {
+            rc = FFR_E_CUDA;
+            break;
+        }
+        unsigned grid = (unsigned)std::min<size_t>((n + 255)/256,(size_t)ds.sm_count*16);
+        add_buffer_kernel<<<grid,256,0,ds.stream>>>(ds.buffer + off,tmp,n,ctx->cellsz);
+        ++ctx->launches;
+        if (!cuda_ok(ctx,cudaStreamSynchronize(ds.stream),"add_buffer_kernel"))
+            rc = FFR_E_CUDA;
+    }
+    cudaFree(tmp);
+    return rc;
+}
+
+int ffr_cuda_clear_buffer(ffr_ctx *ctx)
+{
+    if (!ctx)
+        return FFR_E_INVALID;
+    for (DeviceState &ds : ctx->devs)
+    {
+        CK(cudaSetDevice(ds.dev));
+        CK(cudaMemsetAsync(ds.buffer,0,ctx->bytes,ds.stream));
+        ds.dirty = false;
+    }
+    return sync_all(ctx);
+}
+
+int ffr_cuda_render_chains_async(ffr_ctx *ctx, uint64_t chain_first, uint64_t chain_count,
+        uint64_t chain_len, uint64_t last_len, uint64_t base_seed, uint64_t bv_limit)
+{
+    if (!ctx)
+        return FFR_E_INVALID;
+    if (ctx->devs.size() != 1)
+    {
+        ctx->err = "render_chains_async needs a single device context";
+        return FFR_E_INVALID;
+    }
+    if (chain_len == 0 || last_len > chain_len)
+    {
+        ctx->err = "BufferRenderer::render(): batch size must be positive";
+        return FFR_E_INVALID;
+    }
+    return launch_render(ctx,ctx->devs[0],chain_first,chain_count,chain_len,last_len,base_seed,bv_limit);
+}
+
+int ffr_cuda_sync(ffr_ctx *ctx)
+{
+    if (!ctx)
+        return FFR_E_INVALID;
+    return sync_all(ctx);
+}
+
+int ffr_cuda_get_stats(ffr_ctx *ctx, ffr_stats *stats)
+{
+    if (!ctx || !stats)
+        return FFR_E_INVALID;
+    return collect_stats(ctx,stats);
+}
+
+uint64_t ffr_cuda_launch_count(const ffr_ctx *ctx)
+{
+    return ctx ? ctx->launches : 0;
+}
+
+int ffr_cuda_render_chains(ffr_ctx *ctx, uint64_t chain_first, uint64_t chain_count,
+        uint64_t chain_len, uint64_t last_len, uint64_t base_seed, uint64_t bv_limit,
+        ffr_stats *stats)
+{
+    if (!ctx)
+        return FFR_E_INVALID;
+    if (chain_len == 0 || last_len > chain_len)
+    {
+        ctx->err = "BufferRenderer::render(): batch size must be positive";
+        return FFR_E_INVALID;
+    }
+    const size_t nd = ctx->devs.size();
+    for (DeviceState &ds : ctx->devs)
+    {
+        int rc = reset_bad(ctx,ds);
+        if (rc != FFR_OK)
+            return rc;
+    }
+    /* contiguous chain ranges, one per device */
+    u64 per = (chain_count + nd - 1) / nd;
+    for (size_t i = 0; i < nd; ++i)
+    {
+        u64 first = std::min<u64>(per*i,chain_count);
+        u64 count = std::min<u64>(per,chain_count - first);
+        bool has_last = (first + count == chain_count);
+        int rc = launch_render(ctx,ctx->devs[i],chain_first + first,count,chain_len,
+            has_last ? last_len : 0,base_seed,bv_limit);
+        if (rc != FFR_OK)
+            return rc;
+    }
+    int rc = sync_all(ctx);
+    if (rc != FFR_OK)
+        return rc;
+    ffr_stats local;
+    ffr_stats *st = stats ? stats : &local;
+    rc = collect_stats(ctx,st);
+    if (rc != FFR_OK)
+        return rc;
+    return aborted(ctx,bv_limit,*st) ? FFR_BAD_VALUES : FFR_OK;
+}
+
+int ffr_cuda_render(ffr_ctx *ctx, uint64_t samples, uint64_t chain_len, uint64_t base_seed,
+        uint64_t bv_limit, ffr_progress_cb cb, void *user, ffr_stats *stats)
+{
+    if (!ctx)
+        return FFR_E_INVALID;
+    for (DeviceState &ds : ctx->devs)
+    {
+        int rc = reset_bad(ctx,ds);
+        if (rc != FFR_OK)
+            return rc;
+    }
+    if (samples == 0) /* buffer_renderer.hpp:279-280 */
+    {
+        if (stats)
+            return collect_stats(ctx,stats);
+        return FFR_OK;
+    }
+    if (chain_len < 256) /* :283-285 */
+    {
+        ctx->err = "BufferRenderer::render(): batch size too small";
+        return FFR_E_INVALID;
+    }
+    const u64 chains = (samples + chain_len - 1) / chain_len;
+    const u64 last = samples - (chains - 1)*chain_len;
+    const u64 last_len = (last == chain_len) ? 0 : last;
+    if (!cb)
+        return ffr_cuda_render_chains(ctx,0,chains,chain_len,last_len,base_seed,bv_limit,stats);
+    /* with a progress callback: a few launches, callback after each from this thread */
+    const u64 segs = std::min<u64>(32,std::max<u64>(1,chains / (FFR_TPB*148ULL*4)));
+    const u64 per = (chains + segs - 1) / segs;
+    int rc = FFR_OK;
+    ffr_stats local;
+    ffr_stats *st = stats ? stats : &local;
+    for (u64 first = 0; first < chains; first += per)
+    {
+        u64 count = std::min<u64>(per,chains - first);
+        bool has_last = (first + count == chains);
+        const size_t nd = ctx->devs.size();
+        u64 dper = (count + nd - 1) / nd;
+        for (size_t i = 0; i < nd; ++i)
+        {
+            u64 f = std::min<u64>(dper*i,count);
+            u64 c = std::min<u64>(dper,count - f);
+            rc = launch_render(ctx,ctx->devs[i],first + f,c,chain_len,
+                (has_last && f + c == count) ? last_len : 0,base_seed,bv_limit);
+            if (rc != FFR_OK)
+                return rc;
+        }
+        rc = sync_all(ctx);
+        if (rc != FFR_OK)
+            return rc;
+        rc = collect_stats(ctx,st);
+        if (rc != FFR_OK)
+            return rc;
+        cb(user,first + count,chains);
+        if (aborted(ctx,bv_limit,*st))
+            return FFR_BAD_VALUES;
+    }
+    return FFR_OK;
+}
+
+int ffr_cuda_reduce(ffr_ctx *ctx)
+{
+    if (!ctx)
+        return FFR_E_INVALID;
+    if (ctx->devs.size() < 2)
+        return FFR_OK;
+    DeviceState &d0 = ctx->devs[0];
+    int rc = sync_all(ctx);
+    if (rc != FFR_OK)
+        return rc;
+    const size_t n_elems = ctx->bytes/8;
+    for (size_t i = 1; i < ctx->devs.size(); ++i)
+    {
+        DeviceState &ds = ctx->devs[i];
+        if (!ds.dirty)
+            continue;
+        CK(cudaSetDevice(d0.dev));
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can,d0.dev,ds.dev));
+        const u64 *src = ds.buffer;
+        u64 *staged = nullptr;
+        if (can)
+        {
+            cudaError_t e = cudaDeviceEnablePeerAccess(ds.dev,0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled)
+                cudaGetLastError();
+            else
+                CK(e);
+        }
+        else
+        {
+            /* no NVLink/P2P path between the two: stage through a copy */
+            CK(cudaMalloc(&staged,ctx->bytes));
+            CK(cudaMemcpyPeerAsync(staged,d0.dev,ds.buffer,ds.dev,ctx->bytes,d0.stream));
+            src = staged;
+        }
+        /* device 0 pulls the peer's buffer over NVLink and adds it, typed by position */
+        unsigned grid = (unsigned)std::min<size_t>((n_elems + 255)/256,(size_t)d0.sm_count*16);
+        add_buffer_kernel<<<grid,256,0,d0.stream>>>(d0.buffer,src,n_elems,ctx->cellsz);
+        ++ctx->launches;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(d0.stream));
+        if (staged)
+            cudaFree(staged);
+        /* the peer's samples now live in device 0: clear it so a later reduce adds nothing twice */
+        CK(cudaSetDevice(ds.dev));
+        CK(cudaMemsetAsync(ds.buffer,0,ctx->bytes,ds.stream));
+        CK(cudaStreamSynchronize(ds.stream));
+        ds.dirty = false;
+    }
+    return FFR_OK;
+}
+
+int ffr_cuda_read_buffer(ffr_ctx *ctx, void *host, size_t bytes)
+{
+    if (!ctx || !host)
+        return FFR_E_INVALID;
+    if (bytes != ctx->bytes)
+    {
+        ctx->err = "read_buffer: size mismatch";
+        return FFR_E_INVALID;
+    }
+    int rc = ffr_cuda_reduce(ctx);
+    if (rc != FFR_OK)
+        return rc;
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    CK(cudaMemcpyAsync(host,ds.buffer,bytes,cudaMemcpyDeviceToHost,ds.stream));
+    CK(cudaStreamSynchronize(ds.stream));
+    return FFR_OK;
+}
+
+int ffr_cuda_histogram_sum_max(ffr_ctx *ctx, uint64_t *sum, uint64_t *max)
+{
+    if (!ctx)
+        return FFR_E_INVALID;
+    int rc = ffr_cuda_reduce(ctx);
+    if (rc != FFR_OK)
+        return rc;
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    CK(cudaMemsetAsync(ds.d_scratch,0,2*sizeof(u64),ds.stream));
+    unsigned grid = (unsigned)std::min<u64>((ctx->cells + 255)/256,(u64)ds.sm_count*16);
+    hist_sum_max_kernel<<<grid,256,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,ds.d_scratch,
+        ds.d_scratch+1);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    u64 h[2];
+    CK(cudaMemcpyAsync(h,ds.d_scratch,sizeof(h),cudaMemcpyDeviceToHost,ds.stream));
+    CK(cudaStreamSynchronize(ds.stream));
+    if (sum) *sum = h[0];
+    if (max) *max = h[1];
+    return FFR_OK;
+}
+
+int ffr_cuda_iterate_points(ffr_ctx *ctx, int64_t xf_index, uint64_t n, const uint64_t *seeds,
+        const double *pts_in, double *pts_out)
+{
+    if (!ctx || !seeds || !pts_in || !pts_out)
+        return FFR_E_INVALID;
+    int slot;
+    if (xf_index < 0)
+    {
+        if (!ctx->has_final)
+        {
+            ctx->err = "no final xform";
+            return FFR_E_INVALID;
+        }
+        slot = (int)ctx->num_xforms;
+    }
+    else
+    {
+        if ((u64)xf_index >= ctx->num_xforms)
+        {
+            ctx->err = "xform index out of range";
+            return FFR_E_INVALID;
+        }
+        slot = (int)xf_index;
+    }
+    if (n == 0)
+        return FFR_OK;
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    u64 *d_seeds = nullptr;
+    double *d_in = nullptr, *d_out = nullptr;
+    const size_t pb = n*ctx->dims*sizeof(double);
+    CK(cudaMalloc(&d_seeds,n*8));
+    CK(cudaMalloc(&d_in,pb));
+    CK(cudaMalloc(&d_out,pb));
+    CK(cudaMemcpyAsync(d_seeds,seeds,n*8,cudaMemcpyHostToDevice,ds.stream));
+    CK(cudaMemcpyAsync(d_in,pts_in,pb,cudaMemcpyHostToDevice,ds.stream));
+    const unsigned grid = (unsigned)((n + FFR_TPB - 1)/FFR_TPB);
+    const uint32_t bb = (uint32_t)ctx->blob.size();
+    switch (ctx->dims)
+    {
+    case 1:
+        CK(cudaFuncSetAttribute((const void*)iterate_points_kernel<1>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->smem_bytes));
+        iterate_points_kernel<1><<<grid,FFR_TPB,ctx->smem_bytes,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
+        break;
+    case 2:
+        CK(cudaFuncSetAttribute((const void*)iterate_points_kernel<2>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->smem_bytes));
+        iterate_points_kernel<2><<<grid,FFR_TPB,ctx->smem_bytes,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
+        break;
+    default:
+        CK(cudaFuncSetAttribute((const void*)iterate_points_kernel<3>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->smem_bytes));
+        iterate_points_kernel<3><<<grid,FFR_TPB,ctx->smem_bytes,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
+        break;
+    }
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(pts_out,d_out,pb,cudaMemcpyDeviceToHost,ds.stream));
+    CK(cudaStreamSynchronize(ds.stream));
+    cudaFree(d_seeds);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return FFR_OK;
+}
+
+int ffr_cuda_isaac_words(ffr_ctx *ctx, uint64_t seed, uint64_t n, uint64_t *out)
+{
+    if (!ctx || !out)
+        return FFR_E_INVALID;
+    if (n == 0)
+        return FFR_OK;
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    u64 *d_out = nullptr;
+    CK(cudaMalloc(&d_out,n*8));
+    CK(cudaFuncSetAttribute((const void*)isaac_words_kernel,
+        cudaFuncAttributeMaxDynamicSharedMemorySize,FFR_SMEM_RNG_BYTES));
+    isaac_words_kernel<<<1,FFR_TPB,FFR_SMEM_RNG_BYTES,ds.stream>>>(seed,n,d_out);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out,d_out,n*8,cudaMemcpyDeviceToHost,ds.stream));
+    CK(cudaStreamSynchronize(ds.stream));
+    cudaFree(d_out);
+    return FFR_OK;
+}
+
+int ffr_cuda_atomic_roofline(ffr_ctx *ctx, uint64_t n_atomics, int pattern, float *ms)
+{
+    if (!ctx || !ms)
+        return FFR_E_INVALID;
+    if (pattern != 0)
+    {
+        ctx->err = "atomic_roofline: only pattern 0 (uniform cells) is implemented";
+        return FFR_E_UNSUPPORTED;
+    }
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    const u64 grid = (u64)ds.sm_count * ds.blocks_per_sm;
+    const u64 threads = grid*FFR_TPB;
+    const u64 per_thread = std::max<u64>(1,n_atomics/threads);
+    cudaEvent_t e0,e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0,ds.stream));
+    atomic_bench_kernel<<<(unsigned)grid,FFR_TPB,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,per_thread,
+        0x1234u + ctx->launches);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1,ds.stream));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(ms,e0,e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ds.dirty = true;
+    return FFR_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,439 @@
+/*
+ffr_kernels.cuh -- the render kernel family and its helper kernels (sm_100a).
+
+K1  render_kernel<D,RCAP,AFFINE_ONLY>   chaos game iterate + scatter
+        == BufferRenderer::_render_batch (renderers/buffer_renderer.hpp:150-250) with
+           RenderIterator::_init / iterate (renderers/render_iterator.hpp:52-60,106-139)
+K2  add_buffer_kernel                    addBuffer (buffer_renderer.hpp:375-391), also the
+                                         multi-GPU peer-memory reduce
+K3  hist_sum_max_kernel                  histogramSum / histogramMax (:483-509)
+T1  iterate_points_kernel, isaac_words_kernel   test hooks on the same device functions
+M1  atomic_bench_kernel                  random-atomic microbenchmark (measured scatter roofline)
+
+Execution model of K1: persistent blocks (grid = SMs x resident blocks), FFR_TPB chains per
+block advanced in lock step; a block takes "chain groups" (FFR_TPB consecutive chains) from a
+global work counter until none are left. Chain k is seeded with splitmix64(base_seed + k), so
+the result does not depend on which block, SM or GPU runs it.
+*/
+
+#pragma once
+
+#include "ffr_device.cuh"
+
+struct DevStats
+{
+    u64 s_iter, s_plot;
+    u64 xf_dist[FFR_MAX_XFORMS];       /* by SORTED xform index; host maps to JSON ids */
+    u64 pt_min[3], pt_max[3];          /* f64_to_ordered() keys */
+    u64 n_bad;
+    uint32_t abort, pad;
+    u64 bad_xf[FFR_MAX_BAD_RECORDED];  /* JSON ids */
+    double bad_pt[FFR_MAX_BAD_RECORDED][3];
+};
+
+struct RenderParams
+{
+    const DevFlame *blob;
+    const double *colors;
+    u64 *buffer;
+    DevStats *stats;
+    unsigned int *work_counter;
+    u64 chain_first, chain_count, chain_len, last_len, base_seed, bv_limit;
+    uint32_t blob_bytes, scatter_mode;
+};
+
+#define FFR_SMEM_RNG_BYTES (FFR_RNG_WORDS*FFR_TPB*8)
+
+__device__ __forceinline__ void stage_blob(DevFlame *dst, const DevFlame *src, uint32_t bytes)
+{
+    const u64 *s = (const u64*)src;
+    u64 *d = (u64*)dst;
+    for (uint32_t i = threadIdx.x; i < bytes/8; i += blockDim.x)
+        d[i] = s[i];
+    __syncthreads();
+}
+
+/* colour loops: registers (fully unrolled, predicated) for RCAP <= 4, local memory beyond */
+#define FOR_COLOR(i) _Pragma("unroll") \
+    for (int i = 0; i < (RCAP <= 4 ? RCAP : (int)r); ++i) if (RCAP > 4 || i < (int)r)
+
+template <int D, int RCAP> struct ChainState
+{
+    Rng rng;
+    double p[D];
+    double c[RCAP > 0 ? RCAP : 1];
+};
+
+/* cold path, kept out of line and by value: RenderIterator::init() after a bad value
+   (render_iterator.hpp:52-60 via buffer_renderer.hpp:185) */
+template <int D, int RCAP, bool AFFINE_ONLY>
+__device__ __noinline__ ChainState<D,RCAP> chain_reinit(const DevFlame *fl, Rng rng)
+{
+    ChainState<D,RCAP> st;
+    const DevXForm *xfs = blob_xforms(fl);
+    const DevVar *vars = blob_vars(fl);
+    const uint32_t r = fl->r;
+    double p[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+        p[i] = 2.0*rng.num() - 1.0;
+    for (int s = 0; s < FFR_SETTLE_ITERS; ++s)
+    {
+        uint32_t xi = select_xform(fl,rng);
+        xform_apply<D,AFFINE_ONLY>(xfs[xi],vars,rng,p,p);
+    }
+    FOR_COLOR(i)
+        st.c[i] = rng.num();
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+        st.p[i] = p[i];
+    st.rng = rng;
+    return st;
+}
+
+template <int D, int RCAP, bool AFFINE_ONLY>
+__global__ void __launch_bounds__(FFR_TPB,2) render_kernel(const RenderParams prm)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned int s_group;
+    u64 *rng_base = (u64*)smem;
+    DevFlame *fl = (DevFlame*)(smem + FFR_SMEM_RNG_BYTES);
+    stage_blob(fl,prm.blob,prm.blob_bytes);
+
+    const DevXForm *xfs = blob_xforms(fl);
+    const DevVar *vars = blob_vars(fl);
+    const uint32_t nx = fl->num_xforms;
+    const uint32_t r = fl->r;
+    const uint32_t cellsz = fl->cell;
+    const bool has_final = fl->has_final;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const double *__restrict__ colors = prm.colors;
+    u64 *__restrict__ buffer = prm.buffer;
+    const bool warp_agg = prm.scatter_mode == FFR_SCATTER_WARP_AGG;
+
+    Rng rng;
+    rng.col = rng_base + tid;
+    rng.a = rng.b = rng.c = 0;
+    rng.cnt = 0;
+
+    /* per-thread statistics (buffer_renderer.hpp:156-160), merged at kernel end (:232-246) */
+    u64 n_iter = 0, n_plot = 0;
+    u64 xfc0 = 0, xfc1 = 0;   /* lane i counts selections of xform i (and i+32) for its warp */
+    double pmin[D], pmax[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+    {
+        pmin[i] = INFINITY;
+        pmax[i] = -INFINITY;
+    }
+
+    const u64 num_groups = (prm.chain_count + FFR_TPB - 1) / FFR_TPB;
+    const long long chain_len = (long long)prm.chain_len;
+
+    for (;;)
+    {
+        /* block-uniform: thread 0 takes the next chain group unless the bad value limit
+           was hit (buffer_renderer.hpp:152-153) */
+        if (tid == 0)
+            s_group = (*(volatile uint32_t*)&prm.stats->abort) ? 0xffffffffu
+                                                               : atomicAdd(prm.work_counter,1u);
+        __syncthreads();
+        const u64 g = s_group;
+        __syncthreads();
+        if (g >= num_groups)
+            break;
+        const u64 kk = g*FFR_TPB + tid;
+        const bool active = kk < prm.chain_count;
+        const long long len = !active ? 0 :
+            ((kk+1 == prm.chain_count && prm.last_len) ? (long long)prm.last_len : chain_len);
+        /* rng::setSeed((u64)seed_k) */
+        rng.seed(splitmix64(prm.base_seed + prm.chain_first + kk));
+
+        double p[D], pf[D];
+        double c[RCAP > 0 ? RCAP : 1], cf[RCAP > 0 ? RCAP : 1];
+        bool dead = false;
+        /* RenderIterator::_init: p = randPoint (flame_rng.hpp:151-158) */
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            p[i] = 2.0*rng.num() - 1.0;
+
+        /* iterations -53..-1 are the settle iterations of _init (no stats, no plotting);
+           sharing the loop keeps one inlined copy of the xform interpreter */
+        for (long long it = -FFR_SETTLE_ITERS; it < chain_len; ++it)
+        {
+            if (it == 0 && RCAP > 0)
+            {
+                FOR_COLOR(i)
+                    c[i] = rng.num();
+            }
+            const bool alive = !dead && it < len;
+            uint32_t xi = 0xffffffffu;
+            if (alive)
+            {
+                /* RenderIterator::iterate, render_iterator.hpp:106-139 */
+                xi = select_xform(fl,rng);
+                const DevXForm &xf = xfs[xi];
+                xform_apply<D,AFFINE_ONLY>(xf,vars,rng,p,p);
+                if (it >= 0)
+                {
+                    if (RCAP > 0 && (xf.flags & XF_HAS_COLOR))
+                    {
+                        const double s = xf.color_speed;
+                        FOR_COLOR(i)
+                            c[i] = (1.0-s)*c[i] + s*__ldg(colors + xf.color_off + i);
+                    }
+                    if (has_final)
+                    {
+                        const DevXForm &xff = xfs[nx];
+                        xform_apply<D,AFFINE_ONLY>(xff,vars,rng,p,pf);
+                        if (RCAP > 0)
+                        {
+                            if (xff.flags & XF_HAS_COLOR)
+                            {
+                                const double s = xff.color_speed;
+                                FOR_COLOR(i)
+                                    cf[i] = (1.0-s)*c[i] + s*__ldg(colors + xff.color_off + i);
+                            }
+                            else
+                            {
+                                FOR_COLOR(i)
+                                    cf[i] = c[i];
+                            }
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+                            pf[i] = p[i];
+                        if (RCAP > 0)
+                        {
+                            FOR_COLOR(i)
+                                cf[i] = c[i];
+                        }
+                    }
+                    /* _render_batch body, buffer_renderer.hpp:171-229 */
+                    ++n_iter;
+                    bool bad = false;
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+                        bad |= bad_value(p[i]);
+                    if (bad) /* :175-186 */
+                    {
+                        u64 idx = atomicAdd(&prm.stats->n_bad,1ULL);
+                        if (idx < FFR_MAX_BAD_RECORDED)
+                        {
+                            prm.stats->bad_xf[idx] = xf.json_id;
+#pragma unroll
+                            for (int i = 0; i < D; ++i)
+                                prm.stats->bad_pt[idx][i] = p[i];
+                        }
+                        if (idx + 1 > prm.bv_limit)
+                        {
+                            prm.stats->abort = 1;
+                            dead = true;
+                        }
+                        else
+                        {
+                            /* iter.init(): pf, cf keep their stale values */
+                            ChainState<D,RCAP> st = chain_reinit<D,RCAP,AFFINE_ONLY>(fl,rng);
+                            rng = st.rng;
+#pragma unroll
+                            for (int i = 0; i < D; ++i)
+                                p[i] = st.p[i];
+                            FOR_COLOR(i)
+                                c[i] = st.c[i];
+                        }
+                    }
+                    if (!dead)
+                    {
+#pragma unroll
+                        for (int i = 0; i < D; ++i) /* :188-194 */
+                        {
+                            pmin[i] = (p[i] < pmin[i]) ? p[i] : pmin[i];
+                            pmax[i] = (p[i] > pmax[i]) ? p[i] : pmax[i];
+                        }
+                        /* inclusive bounds on pf (render_iterator.hpp:72-79); NaN is out (Q4) */
+                        bool inb = true;
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+                            inb &= (pf[i] >= fl->lo[i]) && (pf[i] <= fl->hi[i]);
+                        if (inb)
+                        {
+                            ++n_plot;
+                            /* :202-209: truncating double -> index per dimension */
+                            u64 bi = __double2ull_rz((pf[0] - fl->lo[0]) * fl->mult_d[0]);
+#pragma unroll
+                            for (int i = 1; i < D; ++i)
+                                bi += __double2ull_rz((pf[i] - fl->lo[i]) * fl->mult_d[i]) * fl->mult_i[i];
+                            u64 *cell = buffer + bi*cellsz;
+                            if (warp_agg)
+                            {
+                                /* hits of colliding lanes are merged before they leave the SM */
+                                const unsigned peers = __match_any_sync(__activemask(),bi);
+                                if ((int)(__ffs(peers) - 1) == lane)
+                                    atomicAdd(cell,(u64)__popc(peers));
+                            }
+                            else
+                                atomicAdd(cell,1ULL); /* :211-215 */
+                            if (RCAP > 0)
+                            {
+                                FOR_COLOR(i) /* :217-229 */
+                                    atomicAdd((double*)(cell + 1 + i),cf[i]);
+                            }
+                        }
+                    }
+                }
+            }
+            if (it >= 0)
+            {
+                /* ++xf_dist[xf_id] (:172): one ballot per xform, lane i owns xform i's counter */
+                __syncwarp();
+                for (uint32_t i = 0; i < nx; ++i)
+                {
+                    const unsigned m = __ballot_sync(0xffffffffu,xi == i);
+                    if ((uint32_t)lane == (i & 31u))
+                    {
+                        if (i < 32) xfc0 += __popc(m);
+                        else xfc1 += __popc(m);
+                    }
+                }
+            }
+        }
+    }
+
+    /* merge statistics, buffer_renderer.hpp:232-246 */
+    __syncwarp();
+    if ((uint32_t)lane < nx && xfc0)
+        atomicAdd(&prm.stats->xf_dist[lane],xfc0);
+    if ((uint32_t)lane + 32 < nx && xfc1)
+        atomicAdd(&prm.stats->xf_dist[lane+32],xfc1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        n_iter += __shfl_xor_sync(0xffffffffu,n_iter,o);
+        n_plot += __shfl_xor_sync(0xffffffffu,n_plot,o);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+        {
+            double a = __shfl_xor_sync(0xffffffffu,pmin[i],o);
+            double b = __shfl_xor_sync(0xffffffffu,pmax[i],o);
+            pmin[i] = (a < pmin[i]) ? a : pmin[i];
+            pmax[i] = (b > pmax[i]) ? b : pmax[i];
+        }
+    }
+    if (lane == 0)
+    {
+        if (n_iter) atomicAdd(&prm.stats->s_iter,n_iter);
+        if (n_plot) atomicAdd(&prm.stats->s_plot,n_plot);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+        {
+            atomicMin(&prm.stats->pt_min[i],f64_to_ordered(pmin[i]));
+            atomicMax(&prm.stats->pt_max[i],f64_to_ordered(pmax[i]));
+        }
+    }
+}
+
+/* K2: dst += src with the reference's mixed element typing: element 0 of each cell is a u64
+   count, elements 1..r are f64 colour sums (buffer_renderer.hpp:375-391). src may be peer
+   memory (multi-GPU reduce over NVLink) or a staged host buffer (-i). */
+__global__ void add_buffer_kernel(u64 *__restrict__ dst, const u64 *__restrict__ src, u64 n_elems,
+        uint32_t cellsz)
+{
+    const u64 stride = (u64)gridDim.x*blockDim.x;
+    for (u64 i = (u64)blockIdx.x*blockDim.x + threadIdx.x; i < n_elems; i += stride)
+    {
+        const u64 s = src[i];
+        if (cellsz == 1 || i % cellsz == 0)
+            dst[i] += s;
+        else
+            dst[i] = (u64)__double_as_longlong(__longlong_as_double((long long)dst[i])
+                + __longlong_as_double((long long)s));
+    }
+}
+
+/* K3: histogramSum / histogramMax, buffer_renderer.hpp:483-509 */
+__global__ void hist_sum_max_kernel(const u64 *__restrict__ buf, u64 cells, uint32_t cellsz,
+        u64 *out_sum, u64 *out_max)
+{
+    u64 sum = 0, mx = 0;
+    const u64 stride = (u64)gridDim.x*blockDim.x;
+    for (u64 i = (u64)blockIdx.x*blockDim.x + threadIdx.x; i < cells; i += stride)
+    {
+        const u64 v = buf[i*cellsz];
+        sum += v;
+        mx = v > mx ? v : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        sum += __shfl_xor_sync(0xffffffffu,sum,o);
+        const u64 m2 = __shfl_xor_sync(0xffffffffu,mx,o);
+        mx = m2 > mx ? m2 : mx;
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicAdd(out_sum,sum);
+        atomicMax(out_max,mx);
+    }
+}
+
+/* T1: one XForm::applyIteration per point with its own seeded stream */
+template <int D>
+__global__ void __launch_bounds__(FFR_TPB) iterate_points_kernel(const DevFlame *blob,
+        uint32_t blob_bytes, int xf_slot, u64 n, const u64 *seeds, const double *pin, double *pout)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    u64 *rng_base = (u64*)smem;
+    DevFlame *fl = (DevFlame*)(smem + FFR_SMEM_RNG_BYTES);
+    stage_blob(fl,blob,blob_bytes);
+    const u64 i = (u64)blockIdx.x*FFR_TPB + threadIdx.x;
+    if (i >= n)
+        return;
+    Rng rng;
+    rng.col = rng_base + threadIdx.x;
+    rng.seed(seeds[i]);
+    double p[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+        p[d] = pin[i*D+d];
+    xform_apply<D,false>(blob_xforms(fl)[xf_slot],blob_vars(fl),rng,p,p);
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+        pout[i*D+d] = p[d];
+}
+
+/* T1: raw ISAAC stream */
+__global__ void __launch_bounds__(FFR_TPB) isaac_words_kernel(u64 seed, u64 n, u64 *out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    Rng rng;
+    rng.col = (u64*)smem + threadIdx.x;
+    rng.seed(seed + threadIdx.x);
+    if (threadIdx.x == 0)
+        for (u64 i = 0; i < n; ++i)
+            out[i] = rng.next();
+}
+
+/* M1: random-atomic microbenchmark: same RED mix as the render kernel's scatter (1 u64 +
+   r f64 per cell) at uniformly random cells, no chaos game in front of it. */
+__global__ void __launch_bounds__(FFR_TPB) atomic_bench_kernel(u64 *buffer, u64 cells,
+        uint32_t cellsz, u64 per_thread, u64 seed)
+{
+    u64 s = splitmix64(seed + (u64)blockIdx.x*blockDim.x + threadIdx.x);
+    for (u64 k = 0; k < per_thread; ++k)
+    {
+        /* xorshift64* */
+        s ^= s >> 12;
+        s ^= s << 25;
+        s ^= s >> 27;
+        const u64 rnd = s * 0x2545F4914F6CDD1DULL;
+        const u64 bi = __umul64hi(rnd,cells);
+        u64 *cell = buffer + bi*cellsz;
+        atomicAdd(cell,1ULL);
+        for (uint32_t i = 1; i < cellsz; ++i)
+            atomicAdd((double*)(cell + i),0.5);
+    }
+}

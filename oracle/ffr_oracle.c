@@ -1351,6 +1351,16 @@ static u64 chain_iterate(const ffr_flame_desc *fl, isaac64 *rng, chain_state *st
     return xf->id;
 }
 
+/* NaN pf. In the reference a NaN coordinate passes _in_bounds (all comparisons
+   false, render_iterator.hpp:72-79) and then hits an undefined double->size_t cast
+   (buffer_renderer.hpp:202). Default here, and on the device: NaN is out of bounds.
+   With this flag set the oracle instead reproduces what the x86-64 reference binary
+   happens to do (cvttsd2si gives 2^63, which vanishes from the byte offset mod 2^64, so the
+   NaN coordinate contributes 0 to the index and the sample IS counted) -- used only to pin
+   this file against oracle/_ref on flames that produce NaN. */
+static int g_emulate_x86_nan_cast = 0;
+void oracle_set_nan_emulation(int on) { g_emulate_x86_nan_cast = on; }
+
 typedef struct
 {
     const ffr_flame_desc *fl;
@@ -1433,16 +1443,24 @@ static int render_chain(render_target *tg, u64 seed, u64 samples, u64 bv_limit,
            (SURVEY Q4), identical on the device, is: NaN is out of bounds. */
         int inb = 1;
         for (int i = 0; i < D; ++i)
-            if (!(cs.pf[i] >= fl->bounds_lo[i] && cs.pf[i] <= fl->bounds_hi[i]))
+        {
+            if (g_emulate_x86_nan_cast)
+            {
+                if (cs.pf[i] < fl->bounds_lo[i] || cs.pf[i] > fl->bounds_hi[i])
+                    inb = 0;
+            }
+            else if (!(cs.pf[i] >= fl->bounds_lo[i] && cs.pf[i] <= fl->bounds_hi[i]))
                 inb = 0;
+        }
         if (!inb)
             continue;
         ++st->s_plot;
         /* :202-209 */
-        u64 bi = (u64)((cs.pf[0] - fl->bounds_lo[0]) * tg->mult_d[0]);
-        for (int i = 1; i < D; ++i)
+        u64 bi = 0;
+        for (int i = 0; i < D; ++i)
         {
-            u64 di = (u64)((cs.pf[i] - fl->bounds_lo[i]) * tg->mult_d[i]);
+            double sc = (cs.pf[i] - fl->bounds_lo[i]) * tg->mult_d[i];
+            u64 di = isnan(sc) ? 0 : (u64)sc; /* NaN only reachable with the emulation flag */
             bi += di * tg->mult_i[i];
         }
         u64 *bptr = tg->buffer + bi*tg->cell;

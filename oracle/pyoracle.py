@@ -43,6 +43,7 @@ def oracle():
         l.oracle_render_chains.restype = C.c_int
         l.oracle_render_chains.argtypes = [C.POINTER(ffr.FfrFlameDesc)] + [C.c_uint64] * 6 + [
             C.c_void_p, C.POINTER(ffr.FfrStats), C.c_int]
+        l.oracle_set_nan_emulation.argtypes = [C.c_int]
         l.oracle_iterate_points.restype = C.c_int
         l.oracle_iterate_points.argtypes = [C.POINTER(ffr.FfrFlameDesc), C.c_int64, C.c_uint64,
                                             _u64p, _f64p, _f64p]
@@ -104,6 +105,11 @@ def oracle_render(flame, chain_count, chain_len, base_seed=1, chain_first=0, las
     if rc < 0:
         raise RuntimeError("oracle_render_chains failed")
     return buf, ffr.stats_to_dict(st, flame.dims, flame.desc.num_xform_ids), rc == 0
+
+
+def set_nan_emulation(on):
+    """See oracle_set_nan_emulation in ffr_oracle.c: only for pinning against oracle/_ref."""
+    oracle().oracle_set_nan_emulation(1 if on else 0)
 
 
 def oracle_render_samples(flame, samples, chain_len, **kw):

@@ -1,0 +1,40 @@
+"""Quick throughput probe (development aid, not the contract bench): wall clock around
+render_chains for the BASELINE configs. Usage: python tools/probe.py [name ...]"""
+import importlib, sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ffr = importlib.import_module("flame-fractal-renderer_b200")
+ex = importlib.import_module("flame-fractal-renderer_b200.examples")
+
+CONFIGS = {
+    "sierpinski": ("sierpinski_triangle", [1024, 1024]),
+    "barnsley": ("barnsley_fern", [2048, 2048]),
+    "tkoz3": ("tkoz_test3", [4096, 4096]),
+    "sierp3d": ("sierpinski_triangle_3d", [512, 512, 512]),
+    "csci": ("csci6360_project", [4096, 4096]),
+    "csci8k": ("csci6360_project", [8192, 8192]),
+}
+
+def main():
+    names = sys.argv[1:] or list(CONFIGS)
+    L = int(os.environ.get("L", "8192"))
+    waves = int(os.environ.get("WAVES", "2"))
+    modes = [int(m) for m in os.environ.get("MODES", "1").split(",")]
+    bps = int(os.environ.get("BPS", "0"))
+    for nm in names:
+        ename, size = CONFIGS[nm]
+        fl = ffr.Flame(ex.example_json(ename, size=size))
+        for mode in modes:
+            r = ffr.BufferRenderer(fl, scatter_mode=mode, blocks_per_sm=bps)
+            chains = 148 * 2 * 256 * waves
+            r.render_chains(0, 148 * 2 * 256, 256)  # warm-up
+            t0 = time.time()
+            r.render_chains(0, chains, L, base_seed=5)
+            dt = time.time() - t0
+            st = r.stats
+            n = chains * L
+            print("%-10s mode %d  %.3e samples in %.3fs = %.3e samples/s  plotted %.3f" % (
+                nm, mode, n, dt, n / dt, st["s_plot"] / st["s_iter"]), flush=True)
+            r.close()
+
+if __name__ == "__main__":
+    main()
