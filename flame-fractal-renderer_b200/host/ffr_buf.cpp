@@ -1,0 +1,334 @@
+/*
+ffr_buf.cpp -- ffr-buf.out: the reference's buffer renderer command line over libffr_cuda.
+
+Same flags, same buffer file format, same stderr report as the reference's src/ffr_buf.cpp
+(flags :64-73, batch heuristic :94-101, report :104-119 and :226-256, -i handling :168-183,
+output :259-272), so -i buffers still add up and ffr-img.out still reads the output. Boost is
+replaced by getopt_long. Additive flags: --seed (the reference seeds from the clock, so a run
+without --seed does the same), --gpus.
+
+options:
+-h,--help         show usage help message
+-f,--flame        flame json file (required), - for stdin
+-i,--input        input buffers to add at start (repeatable), - for stdin
+-o,--output       output file (required), - for stdout
+-s,--samples      number of samples to render
+-t,--threads      accepted for compatibility; the GPU path does not use host threads
+-b,--batch-size   samples per chain (work unit); 0 = calculate a reasonable size
+-z,--bad-values   number of bad values allowed before terminating render
+   --seed         base seed of the per-chain ISAAC streams (default: clock)
+   --gpus         number of GPUs to shard the chains over (default 1)
+*/
+
+#include "../../include/ffr_flame.h"
+
+#include <getopt.h>
+#include <time.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <iterator>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+static const std::string VERSION = "ffr-b200 0.1";
+
+static void usage()
+{
+    std::cerr <<
+        "ffr-buf usage:\n"
+        "  -h [ --help ]                 show this help message\n"
+        "  -f [ --flame ] arg            flame parameters JSON file\n"
+        "  -i [ --input ] arg            buffers to add initially\n"
+        "  -o [ --output ] arg           output file\n"
+        "  -s [ --samples ] arg (=0)     samples to render\n"
+        "  -t [ --threads ] arg          threads to use (ignored on the GPU path)\n"
+        "  -b [ --batch-size ] arg (=0)  batch size (samples per chain)\n"
+        "  -z [ --bad-values ] arg (=256) bad values limit\n"
+        "  --seed arg                    base seed (default: from the clock)\n"
+        "  --gpus arg (=1)               GPUs to use\n";
+}
+
+static bool read_all(std::istream& is, std::string& out)
+{
+    out.assign(std::istreambuf_iterator<char>(is),std::istreambuf_iterator<char>());
+    return !is.bad();
+}
+
+struct Progress
+{
+    struct timespec t1;
+    uint64_t samples, batch;
+};
+
+static void progress_cb(void *user, uint64_t done, uint64_t total)
+{
+    // same line as ffr_buf.cpp:196-213
+    Progress *p = (Progress*)user;
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC,&t);
+    size_t tn = 1000000000uLL * (t.tv_sec - p->t1.tv_sec) + (t.tv_nsec - p->t1.tv_nsec);
+    size_t tavg = done ? tn / done : 0;
+    size_t trem = tavg * (total - done);
+    double frac = done / (double) total;
+    std::cerr << "\rprogress: " << done << "/" << total << " batches, "
+        << std::min<uint64_t>(p->samples,done*p->batch) << "/" << p->samples << " samples ("
+        << (int)(100*frac) << "%) " << (tn / 1e9) << "sec elapsed, (~"
+        << (trem / 1e9) << "sec remaining)";
+}
+
+int main(int argc, char **argv)
+{
+    size_t arg_threads = std::thread::hardware_concurrency();
+    std::string arg_flame, arg_output;
+    std::vector<std::string> arg_input;
+    size_t arg_samples = 0, arg_batch_size = 0, arg_bad_values = 1 << 8;
+    uint64_t arg_seed = 0;
+    bool have_seed = false;
+    int arg_gpus = 1;
+
+    static const struct option longopts[] = {
+        {"help",no_argument,nullptr,'h'},
+        {"flame",required_argument,nullptr,'f'},
+        {"input",required_argument,nullptr,'i'},
+        {"output",required_argument,nullptr,'o'},
+        {"samples",required_argument,nullptr,'s'},
+        {"threads",required_argument,nullptr,'t'},
+        {"batch-size",required_argument,nullptr,'b'},
+        {"bad-values",required_argument,nullptr,'z'},
+        {"seed",required_argument,nullptr,1000},
+        {"gpus",required_argument,nullptr,1001},
+        {nullptr,0,nullptr,0}
+    };
+    if (argc < 2)
+    {
+        usage();
+        return 1;
+    }
+    int c;
+    while ((c = getopt_long(argc,argv,"hf:i:o:s:t:b:z:",longopts,nullptr)) != -1)
+    {
+        switch (c)
+        {
+        case 'h': usage(); return 1;
+        case 'f': arg_flame = optarg; break;
+        case 'i': arg_input.push_back(optarg); break;
+        case 'o': arg_output = optarg; break;
+        case 's': arg_samples = strtoull(optarg,nullptr,10); break;
+        case 't': arg_threads = strtoull(optarg,nullptr,10); break;
+        case 'b': arg_batch_size = strtoull(optarg,nullptr,10); break;
+        case 'z': arg_bad_values = strtoull(optarg,nullptr,10); break;
+        case 1000: arg_seed = strtoull(optarg,nullptr,0); have_seed = true; break;
+        case 1001: arg_gpus = atoi(optarg); break;
+        default: usage(); return 1;
+        }
+    }
+    if (arg_flame.empty() || arg_output.empty())
+    {
+        std::cerr << "the options '--flame' and '--output' are required" << std::endl;
+        return 1;
+    }
+    if (arg_gpus < 1)
+        arg_gpus = 1;
+
+    // batch size when 0: the reference's clamp((samples+255)>>8, 4096, 1<<20) (ffr_buf.cpp:94-101)
+    // is sized for tens of host threads; a B200 runs ~75k chains at once, so the calculated
+    // size aims at >= 8 chain groups per resident block, still >= the reference's minimum
+    bool calculated_batch_size = false;
+    if (arg_batch_size == 0)
+    {
+        uint64_t resident = (uint64_t)arg_gpus * 148 * 2 * 256;
+        uint64_t guess = (arg_samples + resident*8 - 1) / (resident*8);
+        arg_batch_size = std::clamp<uint64_t>(guess,1<<11,1<<16);
+        calculated_batch_size = true;
+    }
+    if (!have_seed)
+    {
+        // Isaac::setSeed() (isaac.hpp:244-249) seeds from the clock; so does a run without --seed
+        struct timespec t;
+        clock_gettime(CLOCK_REALTIME,&t);
+        arg_seed = (uint64_t)t.tv_sec * 1000000000uLL + t.tv_nsec;
+    }
+
+    std::cerr << "ffr-buf version " << VERSION << std::endl;
+    std::cerr << "--flame " << arg_flame << std::endl;
+    for (auto& s : arg_input)
+        std::cerr << "--input " << s << std::endl;
+    std::cerr << "--output " << arg_output << std::endl;
+    std::cerr << "--samples " << arg_samples;
+    if (arg_samples == 0)
+        std::cerr << " (not rendering)";
+    std::cerr << std::endl;
+    std::cerr << "--threads " << arg_threads << " (unused: " << arg_gpus << " GPU)" << std::endl;
+    if (calculated_batch_size)
+        std::cerr << "--batch_size 0 (" << arg_batch_size << ")" << std::endl;
+    else
+        std::cerr << "--batch_size " << arg_batch_size << std::endl;
+    std::cerr << "--bad_values " << arg_bad_values << std::endl;
+    std::cerr << "--seed " << arg_seed << std::endl;
+    std::cerr << "--" << std::endl;
+
+    std::string text;
+    if (arg_flame == "-")
+    {
+        if (!read_all(std::cin,text))
+            throw std::runtime_error("error reading flame");
+    }
+    else
+    {
+        std::ifstream json_file(arg_flame,std::ios::in|std::ios::binary);
+        if (!json_file || !read_all(json_file,text))
+        {
+            std::cerr << "ERROR: cannot read " << arg_flame << std::endl;
+            return 1;
+        }
+    }
+    char err[512];
+    ffr_flame *flame = ffr_flame_from_json(text.data(),text.size(),err,sizeof(err));
+    if (!flame)
+    {
+        std::cerr << "ERROR: " << err << std::endl;
+        return 1;
+    }
+    const ffr_flame_desc *desc = ffr_flame_get_desc(flame);
+
+    ffr_ctx *ctx = ffr_cuda_create(desc,nullptr,arg_gpus,err,sizeof(err));
+    if (!ctx)
+    {
+        std::cerr << "ERROR: " << err << std::endl;
+        return 1;
+    }
+    const size_t bytes = ffr_cuda_buffer_bytes(ctx);
+    std::cerr << "buffer: " << bytes << " bytes, ";
+#if __BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__
+    std::cerr << "little endian, ";
+#else
+    std::cerr << "big endian, ";
+#endif
+    std::cerr << desc->elem_size << " byte numbers" << std::endl;
+    std::cerr << "size:";
+    for (uint32_t d = 0; d < desc->dims; ++d)
+        std::cerr << " " << desc->size[d];
+    std::cerr << std::endl;
+    std::cerr << "color: " << desc->color_dims << " dimensions" << std::endl;
+
+    std::vector<char> host(bytes);
+
+    // add initial input buffers (ffr_buf.cpp:168-183)
+    for (auto& s : arg_input)
+    {
+        std::cerr << "adding input file " << s << std::endl;
+        bool ok;
+        if (s == "-")
+        {
+            std::cin.read(host.data(),bytes);
+            ok = std::cin.good() || (size_t)std::cin.gcount() == bytes;
+        }
+        else
+        {
+            std::ifstream input_file(s,std::ios::in|std::ios::binary);
+            input_file.read(host.data(),bytes);
+            ok = (size_t)input_file.gcount() == bytes;
+        }
+        if (!ok || ffr_cuda_add_buffer(ctx,host.data(),bytes) != FFR_OK)
+        {
+            std::cerr << "ERROR: error reading file" << std::endl;
+            return 1;
+        }
+    }
+
+    if (arg_samples > 0)
+    {
+        std::cerr << "render start" << std::endl;
+        struct timespec t1,t2;
+        Progress prog;
+        clock_gettime(CLOCK_MONOTONIC,&t1);
+        prog.t1 = t1;
+        prog.samples = arg_samples;
+        prog.batch = arg_batch_size;
+        static ffr_stats stats;
+        int rc = ffr_cuda_render(ctx,arg_samples,arg_batch_size,arg_seed,arg_bad_values,
+            progress_cb,&prog,&stats);
+        // like the reference, the timer spans render() only (ffr_buf.cpp:189-227); the buffer
+        // reduce + copy to the host happens below, as the reference's write does
+        clock_gettime(CLOCK_MONOTONIC,&t2);
+        std::cerr << std::endl;
+        if (rc < 0)
+        {
+            std::cerr << "ERROR: " << ffr_cuda_last_error(ctx) << std::endl;
+            return 1;
+        }
+        size_t nsecs = 1000000000uLL * (t2.tv_sec - t1.tv_sec) + (t2.tv_nsec - t1.tv_nsec);
+        double secs = nsecs / 1e9;
+        if (secs < 1e-9)
+            secs = 1e-9;
+        std::cerr << "render done: " << secs << " sec ("
+            << (size_t)(arg_samples/secs) << " samples/sec)" << std::endl;
+        if (rc == FFR_BAD_VALUES)
+            std::cerr << "render failure "
+                << " (flame may not be sufficiently contractive)" << std::endl;
+        double iter_part = stats.s_iter / (double) arg_samples;
+        std::cerr << "samples iterated: " << stats.s_iter
+            << " (" << (100*iter_part) << "%)" << std::endl;
+        double plot_part = stats.s_plot / (double) arg_samples;
+        std::cerr << "samples plotted: " << stats.s_plot
+            << " (" << (100*plot_part) << "%)" << std::endl;
+        std::cerr << "xform selection:";
+        for (uint32_t i = 0; i < desc->num_xform_ids; ++i)
+            std::cerr << " " << stats.xf_dist[i];
+        std::cerr << std::endl;
+        uint64_t nb = std::min<uint64_t>(stats.n_bad,FFR_MAX_BAD_RECORDED);
+        std::cerr << "bad value xforms:";
+        for (uint64_t i = 0; i < nb; ++i)
+            std::cerr << " " << stats.bad_xf[i];
+        std::cerr << std::endl;
+        std::cerr << "bad value points:";
+        for (uint64_t i = 0; i < nb; ++i)
+        {
+            std::cerr << " (" << stats.bad_pt[i][0];
+            for (uint32_t d = 1; d < desc->dims; ++d)
+                std::cerr << "," << stats.bad_pt[i][d];
+            std::cerr << ")";
+        }
+        std::cerr << std::endl;
+        std::cerr << "extreme coordinates:";
+        for (uint32_t d = 0; d < desc->dims; ++d)
+            std::cerr << " (" << stats.pt_min[d] << "," << stats.pt_max[d] << ")";
+        std::cerr << std::endl;
+    }
+
+    std::cerr << "writing output" << std::endl;
+    if (ffr_cuda_read_buffer(ctx,host.data(),bytes) != FFR_OK)
+    {
+        std::cerr << "ERROR: " << ffr_cuda_last_error(ctx) << std::endl;
+        return 1;
+    }
+    if (arg_output == "-")
+    {
+        std::cout.write(host.data(),bytes);
+        if (!std::cout.good())
+        {
+            std::cerr << "ERROR: error writing output" << std::endl;
+            return 1;
+        }
+    }
+    else
+    {
+        std::ofstream output_file(arg_output,std::ios::out|std::ios::binary);
+        output_file.write(host.data(),bytes);
+        if (!output_file.good())
+        {
+            std::cerr << "ERROR: error writing output" << std::endl;
+            return 1;
+        }
+    }
+    ffr_cuda_destroy(ctx);
+    ffr_flame_free(flame);
+    return 0;
+}

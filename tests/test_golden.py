@@ -1,0 +1,100 @@
+"""The oracle restatement (oracle/ffr_oracle.c) + host flame model against the committed
+golden vectors, which are outputs of the UNMODIFIED reference (tests/golden/make_golden.py).
+Runs anywhere: needs neither /root/reference nor a GPU."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import flames
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "golden.json")) as f:
+    GOLD = json.load(f)
+P = GOLD["params"]
+
+
+def clean(st):
+    def f(x):
+        if isinstance(x, float):
+            return repr(x)
+        if isinstance(x, list):
+            return [f(y) for y in x]
+        return x
+    return {k: f(v) for k, v in st.items() if k not in ("bad_xf", "bad_pt")}
+
+
+def check_case(ffr, po, text, gold):
+    fl = ffr.Flame(text)
+    assert fl.xform_ids == gold["ids"]
+    assert [repr(x) for x in fl.cumulative_weights] == gold["cw"]
+    md, mi, cells, cs = fl.layout()
+    assert [repr(x) for x in md] == gold["mult_d"]
+    assert mi == gold["mult_i"] and cells == gold["cells"] and cs == gold["cell_size"]
+    po.set_nan_emulation(True)  # the reference binary's NaN behaviour, see ffr_oracle.c
+    try:
+        buf, st, ok = po.oracle_render(fl, P["chains"], P["chain_len"], base_seed=P["base_seed"],
+                                       last_len=P["last_len"], bv_limit=1 << 20)
+    finally:
+        po.set_nan_emulation(False)
+    assert ok == gold["ok"]
+    assert clean(st) == gold["stats"]
+    assert hashlib.sha256(buf.tobytes()).hexdigest() == gold["sha256"]
+    assert int(buf.reshape(-1, cs)[:, 0].sum()) == gold["hist_sum"]
+
+
+def test_isaac_known_answers(po):
+    for seed, words in GOLD["isaac"].items():
+        got = ["%016x" % int(x) for x in po.oracle_isaac_words(int(seed), len(words))]
+        assert got == words
+    # SURVEY.md section 4 pins
+    assert GOLD["isaac"]["1"][:4] == ["3dc7e2e12622c959", "262ccb29475eb0cd",
+                                      "62eb77756c571e1a", "326be2ff22a85a27"]
+    assert GOLD["isaac"]["2"][:4] == ["1bd98216b66da880", "7b5eb80a1b3386e0",
+                                      "b394f42a1b0e0eda", "97941dc236c3db23"]
+
+
+def test_survey_md5_pins_recorded():
+    # rng::setSeed(12345 / 999) + renderSeeded(1e7, 1<<20, 256) on sierpinski 512^2
+    assert GOLD["raw_pins"]["12345"] == {"md5": "1d00f9b7761966e8c7244d875f2c0829", "max": 595}
+    assert GOLD["raw_pins"]["999"] == {"md5": "343c317bfdd03a70fac15e645aa029b4", "max": 605}
+
+
+@pytest.mark.parametrize("name", sorted(GOLD["examples"]))
+def test_examples_match_reference(ffr, po, examples, name):
+    size = [48, 48, 48] if name.endswith("3d") else None
+    check_case(ffr, po, examples.example_json(name, size=size), GOLD["examples"][name])
+
+
+@pytest.mark.parametrize("key", sorted(k for k in GOLD["variations"] if "/" in k))
+def test_variations_match_reference(ffr, po, key):
+    name, d = key.split("/")
+    d = int(d)
+    check_case(ffr, po, flames.variation_flame(name, dims=d, final=(d == 3)), GOLD["variations"][key])
+
+
+def test_edge_flames_match_reference(ffr, po):
+    check_case(ffr, po, flames.divergent_flame(), GOLD["variations"]["divergent"])
+    check_case(ffr, po, flames.one_d_flame(), GOLD["variations"]["one_d"])
+    check_case(ffr, po, flames.many_xforms_flame(), GOLD["variations"]["many_xforms"])
+
+
+def test_golden_covers_every_variation():
+    names = {k.split("/")[0] for k in GOLD["variations"] if "/" in k}
+    assert names == set(flames.ALL_VARIATIONS)
+    assert len(names) == 98
+
+
+def test_threaded_oracle_counts_are_exact(ffr, po, examples):
+    fl = ffr.Flame(examples.example_json("tkoz_test3", size=[96, 54]))
+    a, sa, _ = po.oracle_render(fl, 64, 700, base_seed=3, nthreads=1)
+    b, sb, _ = po.oracle_render(fl, 64, 700, base_seed=3, nthreads=8)
+    _, _, cells, cs = fl.layout()
+    ca, cola = ffr.split_counts_colors(a, cells, cs - 1)
+    cb, colb = ffr.split_counts_colors(b, cells, cs - 1)
+    assert np.array_equal(ca, cb)
+    np.testing.assert_allclose(cola, colb, rtol=1e-12, atol=1e-12)
+    for k in ("s_iter", "s_plot", "xf_dist", "pt_min", "pt_max"):
+        assert sa[k] == sb[k]

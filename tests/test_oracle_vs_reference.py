@@ -1,0 +1,61 @@
+"""Live pin of the oracle restatement against the unmodified reference (oracle/_ref), on other
+seeds and sizes than the committed golden vectors. Skipped where _ref was not built."""
+import numpy as np
+import pytest
+
+import flames
+import pyoracle
+
+pytestmark = pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
+
+
+def same(po, ffr, text, chains=16, L=1100, seed=99, last=17):
+    fl = ffr.Flame(text)
+    po.set_nan_emulation(True)
+    try:
+        b1, s1, ok1 = po.oracle_render(fl, chains, L, base_seed=seed, last_len=last, bv_limit=1 << 20)
+    finally:
+        po.set_nan_emulation(False)
+    b2, s2, ok2 = po.ref_render(text, chains, L, base_seed=seed, last_len=last, bv_limit=1 << 20)
+    assert np.array_equal(b1, b2)
+    assert repr(s1) == repr(s2)
+    assert ok1 == ok2
+
+
+def test_isaac_stream(po):
+    for seed in (0, 5, 2**63, 2**64 - 2):
+        assert np.array_equal(po.oracle_isaac_words(seed, 200), po.ref_isaac_words(seed, 200))
+    assert po.oracle().oracle_splitmix64(12345) == po.ref().ref_splitmix64(12345)
+
+
+def test_all_examples(ffr, po, examples):
+    for name in examples.EXAMPLES:
+        size = [40, 40, 40] if name.endswith("3d") else None
+        same(po, ffr, examples.example_json(name, size=size))
+
+
+@pytest.mark.parametrize("name", flames.ALL_VARIATIONS)
+def test_every_variation(ffr, po, name):
+    for d in (2, 3):
+        same(po, ffr, flames.variation_flame(name, dims=d, final=(d == 2)), chains=6, L=900)
+
+
+def test_single_steps(ffr, po):
+    rng = np.random.default_rng(5)
+    for name in ("julian", "supershape", "boarders", "cpow", "lazysusan", "noise"):
+        text = flames.variation_flame(name, dims=2, final=True)
+        fl = ffr.Flame(text)
+        pts = rng.uniform(-3, 3, size=(5000, 2))
+        seeds = rng.integers(0, 2**63, size=5000, dtype=np.uint64)
+        for xi in (0, 1, 2, -1):
+            a = po.oracle_iterate_points(fl, xi, seeds, pts)
+            b = po.ref_iterate_points(text, xi, seeds, pts)
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def test_reference_threaded_render_runs(ffr, po, examples):
+    # the CPU baseline entry point: BufferRenderer::render with threads
+    text = examples.example_json("sierpinski_triangle", size=[64, 64])
+    secs, st, buf = po.ref_render_mt(text, 200_000, 2, 4096, want_buffer=True)
+    assert st["s_iter"] == 200_000 and st["s_plot"] == 200_000
+    assert int(buf.sum()) == 200_000 and secs > 0
