@@ -211,7 +211,9 @@ def main():
 
     # torch owns the device memory and the stream; the library renders into it
     buf = torch.zeros(n_elems, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) stream: handle 0 would mean "library-owned stream" to the ABI
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     rend = ffr.BufferRenderer(flame, devices=[local_rank], external_buffer=buf.data_ptr(),
                               stream=stream.cuda_stream, scatter_mode=args.scatter)
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
