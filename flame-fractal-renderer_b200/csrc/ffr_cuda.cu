@@ -137,7 +137,8 @@ struct ffr_ctx
     u64 cells = 0;
     size_t bytes = 0;
     uint32_t num_xforms = 0, num_ids = 0;
-    bool has_final = false, affine_only = false;
+    bool has_final = false, affine_only = false, regroup = false;
+    uint32_t distinct_oplists = 1;
     std::vector<unsigned char> blob;
     std::vector<double> colors;
     std::vector<u64> json_ids;     /* sorted index -> JSON id */
@@ -182,6 +183,23 @@ render_fn pick_rcap(uint32_t r, bool affine_only)
     if (r == 0) return pick_affine<D,0>(affine_only);
     if (r <= 4) return pick_affine<D,4>(affine_only);
     return pick_affine<D,FFR_MAX_COLOR_DIMS>(affine_only);
+}
+
+/* regroup variant: colour dims <= 4 only */
+render_fn pick_regroup(uint32_t dims, uint32_t r, size_t *extra_smem)
+{
+    const int rc = (r == 0) ? 0 : 4;
+    *extra_smem = FFR_SMEM_REGROUP_BYTES(dims,rc) - FFR_SMEM_RNG_BYTES;
+    switch (dims*10 + rc)
+    {
+    case 10: return (render_fn)render_kernel_regroup<1,0>;
+    case 14: return (render_fn)render_kernel_regroup<1,4>;
+    case 20: return (render_fn)render_kernel_regroup<2,0>;
+    case 24: return (render_fn)render_kernel_regroup<2,4>;
+    case 30: return (render_fn)render_kernel_regroup<3,0>;
+    case 34: return (render_fn)render_kernel_regroup<3,4>;
+    default: return nullptr;
+    }
 }
 
 render_fn pick_kernel(uint32_t dims, uint32_t r, bool affine_only)
@@ -333,6 +351,19 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
             vars.push_back(dv);
         }
         xfs.push_back(dx);
+    }
+    {
+        /* xforms whose variation opcode sequences differ make lanes diverge */
+        std::vector<std::vector<uint32_t>> lists;
+        for (uint32_t i = 0; i < d->num_xforms; ++i)
+        {
+            std::vector<uint32_t> l;
+            for (uint32_t k = 0; k < xfs[i].var_count; ++k)
+                l.push_back(vars[xfs[i].var_begin + k].op);
+            if (std::find(lists.begin(),lists.end(),l) == lists.end())
+                lists.push_back(l);
+        }
+        ctx->distinct_oplists = (uint32_t)lists.size();
     }
     if (ctx->colors.empty())
         ctx->colors.push_back(0.0);
@@ -594,6 +625,20 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
         ctx->scatter_mode = FFR_SCATTER_GLOBAL;
     ctx->kernel = pick_kernel(ctx->dims,ctx->r,ctx->affine_only);
     ctx->smem_bytes = FFR_SMEM_RNG_BYTES + ctx->blob.size();
+    /* regroup (K1b) when lanes would otherwise diverge over different op lists */
+    ctx->regroup = false;
+    if (ctx->opt.regroup != 1 && ctx->r <= 4 && ctx->num_xforms <= 31 &&
+        ((ctx->opt.regroup == 2 && ctx->num_xforms >= 1) || (ctx->distinct_oplists >= 2)))
+    {
+        size_t extra = 0;
+        render_fn k = pick_regroup(ctx->dims,ctx->r,&extra);
+        if (k)
+        {
+            ctx->kernel = k;
+            ctx->smem_bytes = FFR_SMEM_RNG_BYTES + extra + ctx->blob.size();
+            ctx->regroup = true;
+        }
+    }
     ctx->devs.resize(ndev);
     for (int i = 0; i < ndev; ++i)
     {

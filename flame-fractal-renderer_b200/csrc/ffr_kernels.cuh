@@ -336,6 +336,330 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel(const RenderParams pr
     }
 }
 
+/* K1b: the same chain semantics with a per-iteration REGROUP of the block's chains by the
+   xform each one selected, so a warp interprets one op list instead of serialising over every
+   xform its 32 lanes happened to draw (measured on csci6360: 14 variation bodies per
+   warp-iteration instead of 3.2). Chain state (point, colour, generator words) lives in shared
+   memory indexed by chain slot; every iteration
+     A  the slot's OWNER thread draws the xform index from the slot's own ISAAC stream
+     S  counting sort of the 256 slots by xform index (match_any ranks + one warp of prefix sums)
+     B  thread j advances slot perm[j]: xform, final xform, statistics, scatter
+   Which thread advances a chain does not change its arithmetic or its stream, so results are
+   identical to K1 (and to the oracle). Needs num_xforms <= 31 and color_dims <= 4. */
+#define FFR_NWARPS (FFR_TPB/32)
+
+template <int D, int RCAP>
+__global__ void __launch_bounds__(FFR_TPB,2) render_kernel_regroup(const RenderParams prm)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned int s_group;
+    __shared__ unsigned int s_xi[FFR_TPB];
+    __shared__ unsigned short s_perm[FFR_TPB];
+    __shared__ unsigned int s_wcnt[FFR_NWARPS][32];
+    __shared__ unsigned int s_off[FFR_NWARPS][32];
+    u64 *rng_base = (u64*)smem;
+    u64 *st_a = rng_base + FFR_RNG_WORDS*FFR_TPB;    /* randa, randb, randc, randcnt per slot */
+    u64 *st_b = st_a + FFR_TPB;
+    u64 *st_c = st_b + FFR_TPB;
+    u64 *st_n = st_c + FFR_TPB;
+    double *sp = (double*)(st_n + FFR_TPB);          /* p[d][slot] */
+    double *sc = sp + D*FFR_TPB;                     /* c[i][slot], RCAP rows */
+    DevFlame *fl = (DevFlame*)(sc + RCAP*FFR_TPB);
+    stage_blob(fl,prm.blob,prm.blob_bytes);
+
+    const DevXForm *xfs = blob_xforms(fl);
+    const DevVar *vars = blob_vars(fl);
+    const uint32_t nx = fl->num_xforms;
+    const uint32_t r = fl->r;
+    const uint32_t cellsz = fl->cell;
+    const bool has_final = fl->has_final;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const double *__restrict__ colors = prm.colors;
+    u64 *__restrict__ buffer = prm.buffer;
+    const bool warp_agg = prm.scatter_mode == FFR_SCATTER_WARP_AGG;
+
+    u64 n_iter = 0, n_plot = 0;
+    u64 xfc = 0;             /* warp 0, lane k: selections of xform k */
+    double pmin[D], pmax[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+    {
+        pmin[i] = INFINITY;
+        pmax[i] = -INFINITY;
+    }
+
+    const u64 num_groups = (prm.chain_count + FFR_TPB - 1) / FFR_TPB;
+    const long long chain_len = (long long)prm.chain_len;
+
+#define LOAD_RNG(R,slot) do { (R).col = rng_base + (slot); (R).a = st_a[slot]; (R).b = st_b[slot]; \
+        (R).c = st_c[slot]; (R).cnt = (int)st_n[slot]; } while (0)
+#define STORE_RNG(R,slot) do { st_a[slot] = (R).a; st_b[slot] = (R).b; st_c[slot] = (R).c; \
+        st_n[slot] = (u64)(R).cnt; } while (0)
+
+    for (;;)
+    {
+        if (tid == 0)
+            s_group = (*(volatile uint32_t*)&prm.stats->abort) ? 0xffffffffu
+                                                               : atomicAdd(prm.work_counter,1u);
+        __syncthreads();
+        const u64 g = s_group;
+        __syncthreads();
+        if (g >= num_groups)
+            break;
+        const u64 kk = g*FFR_TPB + tid;
+        const bool active = kk < prm.chain_count;
+        const long long len = !active ? 0 :
+            ((kk+1 == prm.chain_count && prm.last_len) ? (long long)prm.last_len : chain_len);
+        bool dead = false;   /* owner-side flag of slot tid */
+        {
+            Rng rng;
+            rng.col = rng_base + tid;
+            rng.seed(splitmix64(prm.base_seed + prm.chain_first + kk));
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                sp[i*FFR_TPB + tid] = 2.0*rng.num() - 1.0;
+            STORE_RNG(rng,tid);
+        }
+        s_xi[tid] = 0;
+
+        for (long long it = -FFR_SETTLE_ITERS; it < chain_len; ++it)
+        {
+            /* ---- A: owner draws ---- */
+            Rng rng;
+            LOAD_RNG(rng,tid);
+            if (it == 0 && RCAP > 0)
+            {
+                FOR_COLOR(i)
+                    sc[i*FFR_TPB + tid] = rng.num();
+            }
+            /* a slot whose chain hit the bad value limit is flagged 0xfffffffe by its worker */
+            dead = dead || (s_xi[tid] == 0xfffffffeu);
+            const bool alive = !dead && it < len;
+            uint32_t key = nx;
+            if (alive)
+                key = select_xform(fl,rng);
+            STORE_RNG(rng,tid);
+            s_xi[tid] = alive ? key : 0xffffffffu;
+            /* ---- S: counting sort of slots by key ---- */
+            s_wcnt[warp][lane] = 0;
+            __syncwarp();
+            const unsigned peers = __match_any_sync(0xffffffffu,key);
+            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            if (rank == 0)
+                s_wcnt[warp][key] = __popc(peers);
+            __syncthreads();
+            if (warp == 0)
+            {
+                unsigned total = 0;
+#pragma unroll
+                for (int w = 0; w < FFR_NWARPS; ++w)
+                {
+                    const unsigned cnt = s_wcnt[w][lane];
+                    s_wcnt[w][lane] = total;      /* exclusive prefix over warps, per key */
+                    total += cnt;
+                }
+                unsigned incl = total;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const unsigned v = __shfl_up_sync(0xffffffffu,incl,o);
+                    if (lane >= o) incl += v;
+                }
+                s_off[0][lane] = incl - total;    /* first position of key `lane` */
+                if (it >= 0 && (uint32_t)lane < nx)
+                    xfc += total;                 /* ++xf_dist[xf_id], buffer_renderer.hpp:172 */
+            }
+            __syncthreads();
+            s_perm[s_off[0][key] + s_wcnt[warp][key] + rank] = (unsigned short)tid;
+            __syncthreads();
+            /* ---- B: advance slot perm[tid] ---- */
+            const int s = s_perm[tid];
+            const uint32_t xi = s_xi[s];
+            if (xi < nx)
+            {
+                const DevXForm &xf = xfs[xi];
+                double p[D], pf[D];
+                double c[RCAP > 0 ? RCAP : 1], cf[RCAP > 0 ? RCAP : 1];
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+                    p[i] = sp[i*FFR_TPB + s];
+                Rng wr;
+                wr.col = rng_base + s;
+                const bool xr = (xf.flags & XF_USES_RNG) || (it >= 0 && has_final && (xfs[nx].flags & XF_USES_RNG));
+                if (xr)
+                    LOAD_RNG(wr,s);
+                /* RenderIterator::iterate, render_iterator.hpp:106-139 */
+                xform_apply<D,false>(xf,vars,wr,p,p);
+                if (it >= 0)
+                {
+                    if (RCAP > 0)
+                    {
+                        FOR_COLOR(i)
+                            c[i] = sc[i*FFR_TPB + s];
+                        if (xf.flags & XF_HAS_COLOR)
+                        {
+                            const double cs = xf.color_speed;
+                            FOR_COLOR(i)
+                                c[i] = (1.0-cs)*c[i] + cs*__ldg(colors + xf.color_off + i);
+                        }
+                    }
+                    if (has_final)
+                    {
+                        const DevXForm &xff = xfs[nx];
+                        xform_apply<D,false>(xff,vars,wr,p,pf);
+                        if (RCAP > 0)
+                        {
+                            if (xff.flags & XF_HAS_COLOR)
+                            {
+                                const double cs = xff.color_speed;
+                                FOR_COLOR(i)
+                                    cf[i] = (1.0-cs)*c[i] + cs*__ldg(colors + xff.color_off + i);
+                            }
+                            else
+                            {
+                                FOR_COLOR(i)
+                                    cf[i] = c[i];
+                            }
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+                            pf[i] = p[i];
+                        if (RCAP > 0)
+                        {
+                            FOR_COLOR(i)
+                                cf[i] = c[i];
+                        }
+                    }
+                    /* _render_batch body, buffer_renderer.hpp:171-229 */
+                    ++n_iter;
+                    bool bad = false;
+                    bool gone = false;
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+                        bad |= bad_value(p[i]);
+                    if (bad) /* :175-186 */
+                    {
+                        u64 idx = atomicAdd(&prm.stats->n_bad,1ULL);
+                        if (idx < FFR_MAX_BAD_RECORDED)
+                        {
+                            prm.stats->bad_xf[idx] = xf.json_id;
+#pragma unroll
+                            for (int i = 0; i < D; ++i)
+                                prm.stats->bad_pt[idx][i] = p[i];
+                        }
+                        if (idx + 1 > prm.bv_limit)
+                        {
+                            prm.stats->abort = 1;
+                            gone = true;
+                            s_xi[s] = 0xfffffffeu;   /* tell the owner this chain stopped */
+                        }
+                        else
+                        {
+                            /* iter.init() on the slot's own stream; pf, cf stay stale (Q3) */
+                            if (!xr)
+                                LOAD_RNG(wr,s);
+                            ChainState<D,RCAP> st = chain_reinit<D,RCAP,false>(fl,wr);
+                            wr = st.rng;
+                            STORE_RNG(wr,s);
+#pragma unroll
+                            for (int i = 0; i < D; ++i)
+                                p[i] = st.p[i];
+                            FOR_COLOR(i)
+                                c[i] = st.c[i];
+                        }
+                    }
+                    else if (xr)
+                        STORE_RNG(wr,s);
+                    if (RCAP > 0)
+                    {
+                        FOR_COLOR(i)
+                            sc[i*FFR_TPB + s] = c[i];
+                    }
+                    if (!gone)
+                    {
+#pragma unroll
+                        for (int i = 0; i < D; ++i) /* :188-194 */
+                        {
+                            pmin[i] = (p[i] < pmin[i]) ? p[i] : pmin[i];
+                            pmax[i] = (p[i] > pmax[i]) ? p[i] : pmax[i];
+                        }
+                        bool inb = true;
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+                            inb &= (pf[i] >= fl->lo[i]) && (pf[i] <= fl->hi[i]);
+                        if (inb)
+                        {
+                            ++n_plot;
+                            u64 bi = __double2ull_rz((pf[0] - fl->lo[0]) * fl->mult_d[0]);
+#pragma unroll
+                            for (int i = 1; i < D; ++i)
+                                bi += __double2ull_rz((pf[i] - fl->lo[i]) * fl->mult_d[i]) * fl->mult_i[i];
+                            u64 *cell = buffer + bi*cellsz;
+                            if (warp_agg)
+                            {
+                                const unsigned pe = __match_any_sync(__activemask(),bi);
+                                if ((int)(__ffs(pe) - 1) == lane)
+                                    atomicAdd(cell,(u64)__popc(pe));
+                            }
+                            else
+                                atomicAdd(cell,1ULL);
+                            if (RCAP > 0)
+                            {
+                                FOR_COLOR(i)
+                                    atomicAdd((double*)(cell + 1 + i),cf[i]);
+                            }
+                        }
+                    }
+                }
+                else if (xr)
+                    STORE_RNG(wr,s);
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+                    sp[i*FFR_TPB + s] = p[i];
+            }
+            __syncthreads();
+        }
+    }
+#undef LOAD_RNG
+#undef STORE_RNG
+
+    /* merge statistics, buffer_renderer.hpp:232-246 */
+    if (warp == 0 && (uint32_t)lane < nx && xfc)
+        atomicAdd(&prm.stats->xf_dist[lane],xfc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        n_iter += __shfl_xor_sync(0xffffffffu,n_iter,o);
+        n_plot += __shfl_xor_sync(0xffffffffu,n_plot,o);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+        {
+            double a = __shfl_xor_sync(0xffffffffu,pmin[i],o);
+            double b = __shfl_xor_sync(0xffffffffu,pmax[i],o);
+            pmin[i] = (a < pmin[i]) ? a : pmin[i];
+            pmax[i] = (b > pmax[i]) ? b : pmax[i];
+        }
+    }
+    if (lane == 0)
+    {
+        if (n_iter) atomicAdd(&prm.stats->s_iter,n_iter);
+        if (n_plot) atomicAdd(&prm.stats->s_plot,n_plot);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+        {
+            atomicMin(&prm.stats->pt_min[i],f64_to_ordered(pmin[i]));
+            atomicMax(&prm.stats->pt_max[i],f64_to_ordered(pmax[i]));
+        }
+    }
+}
+
+#define FFR_SMEM_REGROUP_BYTES(D,RCAP) (FFR_SMEM_RNG_BYTES + 4*FFR_TPB*8 + (D)*FFR_TPB*8 + (RCAP)*FFR_TPB*8)
+
 /* K2: dst += src with the reference's mixed element typing: element 0 of each cell is a u64
    count, elements 1..r are f64 colour sums (buffer_renderer.hpp:375-391). src may be peer
    memory (multi-GPU reduce over NVLink) or a staged host buffer (-i). */

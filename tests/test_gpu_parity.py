@@ -65,11 +65,16 @@ def test_isaac_stream_bit_exact(ffr, po, examples):
     r.close()
 
 
+REGROUP = {"direct": 1, "regroup": 2}  # ffr_options.regroup: 1 = K1 (direct), 2 = K1b forced
+
+
+@pytest.mark.parametrize("kernel", sorted(REGROUP))
 @pytest.mark.parametrize("name", EXACT_EXAMPLES)
-def test_exact_examples(ffr, po, examples, name):
+def test_exact_examples(ffr, po, examples, name, kernel):
     size = [64, 64, 64] if name.endswith("3d") else None
     text = examples.example_json(name, size=size)
-    fl, gbuf, gst, ok, obuf, ost, ook = render_both(ffr, po, text, 1000, 700, seed=11, last_len=123)
+    fl, gbuf, gst, ok, obuf, ost, ook = render_both(ffr, po, text, 1000, 700, seed=11, last_len=123,
+                                                    regroup=REGROUP[kernel])
     assert ok and ook
     assert_stats_equal(gst, ost)
     assert_buffers(ffr, fl, gbuf, obuf)
@@ -85,38 +90,46 @@ def test_scatter_modes_bit_exact(ffr, po, examples, mode):
     assert_buffers(ffr, fl, gbuf, obuf)
 
 
+@pytest.mark.parametrize("kernel", sorted(REGROUP))
 @pytest.mark.parametrize("name", flames.IEEE_EXACT)
 @pytest.mark.parametrize("dims", [2, 3])
-def test_ieee_only_variations_bit_exact(ffr, po, name, dims):
+def test_ieee_only_variations_bit_exact(ffr, po, name, dims, kernel):
     if dims == 3 and name not in flames.PARAMS_ND and name not in ("horseshoe", "curl", "boarders"):
         pytest.skip("3-d lifting covered by a subset")
     text = flames.variation_flame(name, dims=dims, final=(dims == 3))
-    fl, gbuf, gst, ok, obuf, ost, ook = render_both(ffr, po, text, 300, 512, seed=3, bv_limit=1 << 40)
+    fl, gbuf, gst, ok, obuf, ost, ook = render_both(ffr, po, text, 300, 512, seed=3, bv_limit=1 << 40,
+                                                    regroup=REGROUP[kernel])
     assert_stats_equal(gst, ost)
     assert_buffers(ffr, fl, gbuf, obuf)
 
 
+@pytest.mark.parametrize("kernel", sorted(REGROUP))
 @pytest.mark.parametrize("name", [n for n in flames.PARAMS_ND if n in flames.IEEE_EXACT])
-def test_one_d_bit_exact(ffr, po, name):
+def test_one_d_bit_exact(ffr, po, name, kernel):
     text = flames.variation_flame(name, dims=1)
-    fl, gbuf, gst, ok, obuf, ost, ook = render_both(ffr, po, text, 300, 512, seed=9, bv_limit=1 << 40)
+    fl, gbuf, gst, ok, obuf, ost, ook = render_both(ffr, po, text, 300, 512, seed=9, bv_limit=1 << 40,
+                                                    regroup=REGROUP[kernel])
     assert_stats_equal(gst, ost)
     assert_buffers(ffr, fl, gbuf, obuf)
 
 
-def test_edge_flames_bit_exact(ffr, po):
+@pytest.mark.parametrize("kernel", sorted(REGROUP))
+def test_edge_flames_bit_exact(ffr, po, kernel):
     for text in (flames.one_d_flame(), flames.many_xforms_flame()):
-        fl, gbuf, gst, ok, obuf, ost, ook = render_both(ffr, po, text, 520, 300, seed=21)
+        fl, gbuf, gst, ok, obuf, ost, ook = render_both(ffr, po, text, 520, 300, seed=21,
+                                                        regroup=REGROUP[kernel])
         assert_stats_equal(gst, ost)
         assert_buffers(ffr, fl, gbuf, obuf)
 
 
-def test_bad_values_reinit_bit_exact(ffr, po):
+@pytest.mark.parametrize("kernel", sorted(REGROUP))
+def test_bad_values_reinit_bit_exact(ffr, po, kernel):
     """Expanding map: thousands of bad values, each re-initialising its chain from the
     chain's own stream (buffer_renderer.hpp:175-186). With the limit out of reach
     every count must still match the oracle bit for bit."""
     text = flames.divergent_flame()
-    fl, gbuf, gst, ok, obuf, ost, ook = render_both(ffr, po, text, 300, 400, seed=2, bv_limit=1 << 40)
+    fl, gbuf, gst, ok, obuf, ost, ook = render_both(ffr, po, text, 300, 400, seed=2, bv_limit=1 << 40,
+                                                    regroup=REGROUP[kernel])
     assert ost["n_bad"] > 1000
     assert ok and ook
     assert_stats_equal(gst, ost)
@@ -125,9 +138,10 @@ def test_bad_values_reinit_bit_exact(ffr, po):
     assert len(gst["bad_xf"]) == ffr.FFR_MAX_BAD_RECORDED
 
 
-def test_bad_value_limit_aborts(ffr, po):
+@pytest.mark.parametrize("kernel", sorted(REGROUP))
+def test_bad_value_limit_aborts(ffr, po, kernel):
     fl = ffr.Flame(flames.divergent_flame())
-    r = ffr.BufferRenderer(fl)
+    r = ffr.BufferRenderer(fl, regroup=REGROUP[kernel])
     ok = r.render(300 * 400, 400, base_seed=2, bv_limit=16)
     assert not ok  # render() returns false (buffer_renderer.hpp:308-314)
     assert r.stats["n_bad"] > 16

@@ -20,11 +20,12 @@ def main():
     waves = int(os.environ.get("WAVES", "2"))
     modes = [int(m) for m in os.environ.get("MODES", "1").split(",")]
     bps = int(os.environ.get("BPS", "0"))
+    regs = [int(m) for m in os.environ.get("REGROUP", "0").split(",")]
     for nm in names:
         ename, size = CONFIGS[nm]
         fl = ffr.Flame(ex.example_json(ename, size=size))
-        for mode in modes:
-            r = ffr.BufferRenderer(fl, scatter_mode=mode, blocks_per_sm=bps)
+        for mode, rg in [(m, g) for m in modes for g in regs]:
+            r = ffr.BufferRenderer(fl, scatter_mode=mode, blocks_per_sm=bps, regroup=rg)
             chains = 148 * 2 * 256 * waves
             r.render_chains(0, 148 * 2 * 256, 256)  # warm-up
             t0 = time.time()
@@ -32,8 +33,8 @@ def main():
             dt = time.time() - t0
             st = r.stats
             n = chains * L
-            print("%-10s mode %d  %.3e samples in %.3fs = %.3e samples/s  plotted %.3f" % (
-                nm, mode, n, dt, n / dt, st["s_plot"] / st["s_iter"]), flush=True)
+            print("%-10s mode %d rg %d  %.3e samples in %.3fs = %.3e samples/s  plotted %.3f" % (
+                nm, mode, rg, n, dt, n / dt, st["s_plot"] / st["s_iter"]), flush=True)
             r.close()
 
 if __name__ == "__main__":

@@ -1,0 +1,15 @@
+"""One render launch for ncu (development aid). Usage: prof_one.py workload regroup [waves] [L]"""
+import importlib, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ffr = importlib.import_module("flame-fractal-renderer_b200")
+ex = importlib.import_module("flame-fractal-renderer_b200.examples")
+from probe import CONFIGS
+nm, rg = sys.argv[1], int(sys.argv[2])
+waves = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+L = int(sys.argv[4]) if len(sys.argv) > 4 else 2048
+ename, size = CONFIGS[nm]
+fl = ffr.Flame(ex.example_json(ename, size=size))
+r = ffr.BufferRenderer(fl, regroup=rg)
+r.render_chains(0, 148 * 2 * 256, 256)
+r.render_chains(0, 148 * 2 * 256 * waves, L, base_seed=5)
+print(r.stats["s_iter"])
