@@ -356,7 +356,6 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel_regroup(const RenderP
     __shared__ unsigned int s_xi[FFR_TPB];
     __shared__ unsigned short s_perm[FFR_TPB];
     __shared__ unsigned int s_wcnt[FFR_NWARPS][32];
-    __shared__ unsigned int s_off[FFR_NWARPS][32];
     u64 *rng_base = (u64*)smem;
     u64 *st_a = rng_base + FFR_RNG_WORDS*FFR_TPB;    /* randa, randb, randc, randcnt per slot */
     u64 *st_b = st_a + FFR_TPB;
@@ -450,14 +449,15 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel_regroup(const RenderP
             if (rank == 0)
                 s_wcnt[warp][key] = __popc(peers);
             __syncthreads();
-            if (warp == 0)
             {
-                unsigned total = 0;
+                /* every warp computes the same prefix sums (lane = key) instead of one warp
+                   computing them for all behind another barrier */
+                unsigned total = 0, before = 0;
 #pragma unroll
                 for (int w = 0; w < FFR_NWARPS; ++w)
                 {
                     const unsigned cnt = s_wcnt[w][lane];
-                    s_wcnt[w][lane] = total;      /* exclusive prefix over warps, per key */
+                    if (w < warp) before += cnt;  /* same-key slots in earlier warps */
                     total += cnt;
                 }
                 unsigned incl = total;
@@ -467,12 +467,12 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel_regroup(const RenderP
                     const unsigned v = __shfl_up_sync(0xffffffffu,incl,o);
                     if (lane >= o) incl += v;
                 }
-                s_off[0][lane] = incl - total;    /* first position of key `lane` */
-                if (it >= 0 && (uint32_t)lane < nx)
+                const unsigned first = incl - total + before; /* first position of (key=lane, this warp) */
+                if (warp == 0 && it >= 0 && (uint32_t)lane < nx)
                     xfc += total;                 /* ++xf_dist[xf_id], buffer_renderer.hpp:172 */
+                const unsigned mypos = __shfl_sync(0xffffffffu,first,key) + rank;
+                s_perm[mypos] = (unsigned short)tid;
             }
-            __syncthreads();
-            s_perm[s_off[0][key] + s_wcnt[warp][key] + rank] = (unsigned short)tid;
             __syncthreads();
             /* ---- B: advance slot perm[tid] ---- */
             const int s = s_perm[tid];

@@ -1,0 +1,104 @@
+"""Multi-GPU paths on hardware (skipped with fewer than 2 devices): the single-process
+multi-device context (chain-range sharding + peer-memory reduce inside libffr_cuda, the
+ffr-buf.out --gpus path) must give the same buffer as one device, bit for bit for counts."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ndev(ffr):
+    return ffr.lib().ffr_cuda_device_count()
+
+
+@pytest.mark.parametrize("name,size", [("barnsley_fern", [256, 256]), ("tkoz_test3", [160, 90])])
+def test_two_devices_equal_one(ffr, po, examples, name, size):
+    if _ndev(ffr) < 2:
+        pytest.skip("needs 2 GPUs")
+    fl = ffr.Flame(examples.example_json(name, size=size))
+    _, _, cells, cs = fl.layout()
+    r1 = ffr.BufferRenderer(fl, devices=[0])
+    assert r1.render(3_000_000, 1000, base_seed=8)
+    b1 = r1.read_buffer()
+    s1 = r1.stats
+    r1.close()
+    r2 = ffr.BufferRenderer(fl, devices=[0, 1])
+    assert r2.render(3_000_000, 1000, base_seed=8)
+    b2 = r2.read_buffer()
+    s2 = r2.stats
+    # a second read must not add the peer buffer twice
+    b2b = r2.read_buffer()
+    r2.close()
+    assert np.array_equal(b2, b2b)
+    c1, col1 = ffr.split_counts_colors(b1, cells, cs - 1)
+    c2, col2 = ffr.split_counts_colors(b2, cells, cs - 1)
+    if name == "barnsley_fern":
+        assert np.array_equal(c1, c2)
+        for k in ("s_iter", "s_plot", "xf_dist", "pt_min", "pt_max"):
+            assert s1[k] == s2[k]
+        want, _, _ = po.oracle_render_samples(fl, 3_000_000, 1000, base_seed=8, nthreads=8)
+        assert np.array_equal(b2, want)
+    else:
+        # same chains, same device code on both GPUs: counts identical, colours to rounding
+        assert np.array_equal(c1, c2)
+        np.testing.assert_allclose(col1, col2, rtol=1e-12, atol=1e-9)
+
+
+def test_add_buffer_resume(ffr, po, examples):
+    """-i semantics (buffer_renderer.hpp:375-452): counts add as integers, colours as floats."""
+    fl = ffr.Flame(examples.example_json("tkoz_test3", size=[96, 54]))
+    _, _, cells, cs = fl.layout()
+    r = ffr.BufferRenderer(fl)
+    r.render_chains(0, 300, 512, base_seed=3)
+    first = r.read_buffer().copy()
+    r.clear()
+    r.add_buffer(first)
+    r.add_buffer(first)
+    twice = r.read_buffer()
+    r.close()
+    c1, col1 = ffr.split_counts_colors(first, cells, cs - 1)
+    c2, col2 = ffr.split_counts_colors(twice, cells, cs - 1)
+    assert np.array_equal(c2, 2 * c1)
+    np.testing.assert_array_equal(col2, col1 + col1)
+    assert r.bytes == first.nbytes
+
+
+def test_histogram_sum_max_and_progress(ffr, examples):
+    fl = ffr.Flame(examples.example_json("sierpinski_triangle", size=[128, 128]))
+    r = ffr.BufferRenderer(fl)
+    calls = []
+    assert r.render(2_000_000, 512, base_seed=1, progress=lambda d, t: calls.append((d, t)))
+    buf = r.read_buffer()
+    s, m = r.histogram_sum_max()
+    assert s == int(buf.sum()) == 2_000_000 == r.stats["s_plot"]
+    assert m == int(buf.max())
+    assert calls and calls[-1][0] == calls[-1][1] == (2_000_000 + 511) // 512
+    # render() argument checks of the reference (buffer_renderer.hpp:279-285)
+    with pytest.raises(ffr.FfrError, match="batch size too small"):
+        r.render(1000, 255)
+    assert r.render(0, 4096)
+    r.close()
+
+
+def test_ffr_buf_cli_roundtrip(ffr, po, examples, tmp_path):
+    """ffr-buf.out: same flags and buffer file format; -i adds the previous output."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(ffr.LIB_PATH), "ffr-buf.out")
+    flame = tmp_path / "fern.json"
+    flame.write_text(examples.example_json("barnsley_fern", size=[200, 100]))
+    out1 = tmp_path / "a.buf"
+    out2 = tmp_path / "b.buf"
+    p = subprocess.run([exe, "-f", str(flame), "-o", str(out1), "-s", "1500000", "-b", "1000",
+                        "--seed", "5", "-t", "3"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "samples plotted: 1500000" in p.stderr and "samples/sec" in p.stderr
+    a = np.fromfile(out1, dtype=np.uint64)
+    fl = ffr.Flame(flame.read_text())
+    want, _, _ = po.oracle_render_samples(fl, 1_500_000, 1000, base_seed=5, nthreads=8)
+    assert np.array_equal(a, want)
+    p = subprocess.run([exe, "-f", str(flame), "-i", str(out1), "-i", str(out1), "-o", str(out2),
+                        "-s", "0"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "(not rendering)" in p.stderr
+    assert np.array_equal(np.fromfile(out2, dtype=np.uint64), 2 * a)
