@@ -216,10 +216,8 @@ def main():
     torch.cuda.set_stream(stream)
     rend = ffr.BufferRenderer(flame, devices=[local_rank], external_buffer=buf.data_ptr(),
                               stream=stream.cuda_stream, scatter_mode=args.scatter)
-    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-    # one wave = every resident block takes one chain group of 256 chains
-    resident_groups = sm_count * 2
-    chains_per_step = resident_groups * 256 * args.waves
+    # one wave = every resident block (SMs x blocks/SM) takes one chain group of 256 chains
+    chains_per_step = rend.resident_chains * args.waves
     samples_per_step = chains_per_step * L
 
     def barrier():

@@ -130,6 +130,7 @@ ABI = {
                                                C.c_uint64, C.c_uint64, C.c_uint64]),
     "ffr_cuda_sync": (C.c_int, [C.c_void_p]),
     "ffr_cuda_get_stats": (C.c_int, [C.c_void_p, C.POINTER(FfrStats)]),
+    "ffr_cuda_resident_chains": (C.c_uint64, [C.c_void_p]),
     "ffr_cuda_launch_count": (C.c_uint64, [C.c_void_p]),
     "ffr_cuda_reduce": (C.c_int, [C.c_void_p]),
     "ffr_cuda_read_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -316,6 +317,10 @@ class BufferRenderer:
     @property
     def stats(self):
         return stats_to_dict(self._stats, self.flame.dims, self.flame.desc.num_xform_ids)
+
+    @property
+    def resident_chains(self):
+        return lib().ffr_cuda_resident_chains(self._h)
 
     @property
     def launches(self):

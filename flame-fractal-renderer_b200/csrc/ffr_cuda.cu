@@ -122,6 +122,7 @@ struct DeviceState
     DevStats *d_stats = nullptr;
     unsigned int *d_counter = nullptr;
     u64 *d_scratch = nullptr;      /* 2 x u64 for histogram sum/max */
+    u64 *d_rsl = nullptr;          /* K1b randrsl scratch */
     int sm_count = 0;
     int blocks_per_sm = 0;
     bool dirty = false;            /* holds samples not yet reduced into device 0 */
@@ -189,7 +190,7 @@ render_fn pick_rcap(uint32_t r, bool affine_only)
 render_fn pick_regroup(uint32_t dims, uint32_t r, size_t *extra_smem)
 {
     const int rc = (r == 0) ? 0 : 4;
-    *extra_smem = FFR_SMEM_REGROUP_BYTES(dims,rc) - FFR_SMEM_RNG_BYTES;
+    *extra_smem = FFR_SMEM_REGROUP_BYTES(dims,rc);
     switch (dims*10 + rc)
     {
     case 10: return (render_fn)render_kernel_regroup<1,0>;
@@ -272,8 +273,8 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
     }
     hdr.cells = cells;
     hdr.cell = 1 + d->color_dims;
-    for (uint32_t i = 0; i < d->num_xforms; ++i)
-        hdr.xfcw[i] = d->xfcw[i];
+    for (uint32_t i = 0; i < FFR_MAX_XFORMS; ++i)
+        hdr.xfcw[i] = (i < d->num_xforms) ? d->xfcw[i] : 2.0; /* padding never < r, see select_xform */
 
     std::vector<DevXForm> xfs;
     std::vector<DevVar> vars;
@@ -459,6 +460,8 @@ int setup_device(ffr_ctx *ctx, DeviceState &ds, int dev, const ffr_options &opt)
     if (opt.blocks_per_sm && (int)opt.blocks_per_sm < nb)
         nb = (int)opt.blocks_per_sm;
     ds.blocks_per_sm = nb;
+    if (ctx->regroup)
+        CK(cudaMalloc(&ds.d_rsl,(size_t)ds.sm_count*nb*16*FFR_TPB*sizeof(u64)));
     CK(cudaStreamSynchronize(ds.stream));
     return FFR_OK;
 }
@@ -475,6 +478,7 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
     prm.buffer = ds.buffer;
     prm.stats = ds.d_stats;
     prm.work_counter = ds.d_counter;
+    prm.rsl_scratch = ds.d_rsl;
     prm.chain_first = chain_first;
     prm.chain_count = chain_count;
     prm.chain_len = chain_len;
@@ -635,7 +639,7 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
         if (k)
         {
             ctx->kernel = k;
-            ctx->smem_bytes = FFR_SMEM_RNG_BYTES + extra + ctx->blob.size();
+            ctx->smem_bytes = extra + ctx->blob.size();
             ctx->regroup = true;
         }
     }
@@ -669,6 +673,7 @@ void ffr_cuda_destroy(ffr_ctx *ctx)
         if (ds.d_stats) cudaFree(ds.d_stats);
         if (ds.d_counter) cudaFree(ds.d_counter);
         if (ds.d_scratch) cudaFree(ds.d_scratch);
+        if (ds.d_rsl) cudaFree(ds.d_rsl);
         if (ds.own_stream && ds.stream) cudaStreamDestroy(ds.stream);
     }
     delete ctx;
@@ -776,6 +781,13 @@ int ffr_cuda_get_stats(ffr_ctx *ctx, ffr_stats *stats)
     if (!ctx || !stats)
         return FFR_E_INVALID;
     return collect_stats(ctx,stats);
+}
+
+uint64_t ffr_cuda_resident_chains(const ffr_ctx *ctx)
+{
+    if (!ctx || ctx->devs.empty())
+        return 0;
+    return (uint64_t)ctx->devs[0].sm_count * ctx->devs[0].blocks_per_sm * FFR_TPB;
 }
 
 uint64_t ffr_cuda_launch_count(const ffr_ctx *ctx)
@@ -1018,22 +1030,23 @@ int ffr_cuda_iterate_points(ffr_ctx *ctx, int64_t xf_index, uint64_t n, const ui
     CK(cudaMemcpyAsync(d_in,pts_in,pb,cudaMemcpyHostToDevice,ds.stream));
     const unsigned grid = (unsigned)((n + FFR_TPB - 1)/FFR_TPB);
     const uint32_t bb = (uint32_t)ctx->blob.size();
+    const size_t sm = FFR_SMEM_RNG_BYTES + ctx->blob.size();
     switch (ctx->dims)
     {
     case 1:
         CK(cudaFuncSetAttribute((const void*)iterate_points_kernel<1>,
-            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->smem_bytes));
-        iterate_points_kernel<1><<<grid,FFR_TPB,ctx->smem_bytes,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
+            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)sm));
+        iterate_points_kernel<1><<<grid,FFR_TPB,sm,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
         break;
     case 2:
         CK(cudaFuncSetAttribute((const void*)iterate_points_kernel<2>,
-            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->smem_bytes));
-        iterate_points_kernel<2><<<grid,FFR_TPB,ctx->smem_bytes,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
+            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)sm));
+        iterate_points_kernel<2><<<grid,FFR_TPB,sm,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
         break;
     default:
         CK(cudaFuncSetAttribute((const void*)iterate_points_kernel<3>,
-            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->smem_bytes));
-        iterate_points_kernel<3><<<grid,FFR_TPB,ctx->smem_bytes,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
+            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)sm));
+        iterate_points_kernel<3><<<grid,FFR_TPB,sm,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
         break;
     }
     ++ctx->launches;

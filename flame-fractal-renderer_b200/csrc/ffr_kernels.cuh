@@ -38,6 +38,7 @@ struct RenderParams
     u64 *buffer;
     DevStats *stats;
     unsigned int *work_counter;
+    u64 *rsl_scratch;              /* K1b: randrsl columns, 16*FFR_TPB words per block */
     u64 chain_first, chain_count, chain_len, last_len, base_seed, bv_limit;
     uint32_t blob_bytes, scatter_mode;
 };
@@ -92,7 +93,7 @@ __device__ __noinline__ ChainState<D,RCAP> chain_reinit(const DevFlame *fl, Rng 
 }
 
 template <int D, int RCAP, bool AFFINE_ONLY>
-__global__ void __launch_bounds__(FFR_TPB,2) render_kernel(const RenderParams prm)
+__global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : 2) render_kernel(const RenderParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned int s_group;
@@ -113,13 +114,21 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel(const RenderParams pr
     const bool warp_agg = prm.scatter_mode == FFR_SCATTER_WARP_AGG;
 
     Rng rng;
-    rng.col = rng_base + tid;
+    rng.bind(rng_base,tid);
     rng.a = rng.b = rng.c = 0;
     rng.cnt = 0;
 
     /* per-thread statistics (buffer_renderer.hpp:156-160), merged at kernel end (:232-246) */
     u64 n_iter = 0, n_plot = 0;
     u64 xfc0 = 0, xfc1 = 0;   /* lane i counts selections of xform i (and i+32) for its warp */
+    /* up to 8 xforms: ++xf_dist[xf_id] as 16-bit fields packed in two registers per thread,
+       flushed to shared counters every 32768 iterations (one ballot per xform otherwise) */
+    __shared__ unsigned long long s_xf[8];
+    const bool packed_xf = nx <= 8;
+    u64 pk0 = 0, pk1 = 0;
+    if (tid < 8)
+        s_xf[tid] = 0;
+    __syncthreads();
     double pmin[D], pmax[D];
 #pragma unroll
     for (int i = 0; i < D; ++i)
@@ -286,7 +295,26 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel(const RenderParams pr
                     }
                 }
             }
-            if (it >= 0)
+            if (it >= 0 && packed_xf)
+            {
+                /* xi == 0xffffffff (not alive) matches neither range */
+                const u64 inc = 1ULL << ((xi & 3u)*16u);
+                pk0 += (xi < 4u) ? inc : 0ULL;
+                pk1 += (xi - 4u < 4u) ? inc : 0ULL;
+                if ((it & 0x7fff) == 0x7fff || it == chain_len - 1)
+                {
+#pragma unroll
+                    for (int f = 0; f < 4; ++f)
+                    {
+                        const unsigned a0 = (unsigned)((pk0 >> (16*f)) & 0xffffu);
+                        const unsigned a1 = (unsigned)((pk1 >> (16*f)) & 0xffffu);
+                        if (a0) atomicAdd(&s_xf[f],(unsigned long long)a0);
+                        if (a1) atomicAdd(&s_xf[4+f],(unsigned long long)a1);
+                    }
+                    pk0 = pk1 = 0;
+                }
+            }
+            else if (it >= 0)
             {
                 /* ++xf_dist[xf_id] (:172): one ballot per xform, lane i owns xform i's counter */
                 __syncwarp();
@@ -304,6 +332,9 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel(const RenderParams pr
     }
 
     /* merge statistics, buffer_renderer.hpp:232-246 */
+    __syncthreads();
+    if (packed_xf && (uint32_t)tid < nx && s_xf[tid])
+        atomicAdd(&prm.stats->xf_dist[tid],s_xf[tid]);
     __syncwarp();
     if ((uint32_t)lane < nx && xfc0)
         atomicAdd(&prm.stats->xf_dist[lane],xfc0);
@@ -347,17 +378,21 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel(const RenderParams pr
    Which thread advances a chain does not change its arithmetic or its stream, so results are
    identical to K1 (and to the oracle). Needs num_xforms <= 31 and color_dims <= 4. */
 #define FFR_NWARPS (FFR_TPB/32)
+#ifndef FFR_REGROUP_MINB
+#define FFR_REGROUP_MINB 3
+#endif
 
 template <int D, int RCAP>
-__global__ void __launch_bounds__(FFR_TPB,2) render_kernel_regroup(const RenderParams prm)
+__global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regroup(const RenderParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned int s_group;
     __shared__ unsigned int s_xi[FFR_TPB];
     __shared__ unsigned short s_perm[FFR_TPB];
     __shared__ unsigned int s_wcnt[FFR_NWARPS][32];
-    u64 *rng_base = (u64*)smem;
-    u64 *st_a = rng_base + FFR_RNG_WORDS*FFR_TPB;    /* randa, randb, randc, randcnt per slot */
+    u64 *rng_base = (u64*)smem;                      /* randmem columns only (16 words/slot) */
+    u64 *rsl_base = prm.rsl_scratch + (size_t)blockIdx.x*16*FFR_TPB; /* randrsl: L2-resident */
+    u64 *st_a = rng_base + 16*FFR_TPB;               /* randa, randb, randc, randcnt per slot */
     u64 *st_b = st_a + FFR_TPB;
     u64 *st_c = st_b + FFR_TPB;
     u64 *st_n = st_c + FFR_TPB;
@@ -392,7 +427,7 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel_regroup(const RenderP
     const u64 num_groups = (prm.chain_count + FFR_TPB - 1) / FFR_TPB;
     const long long chain_len = (long long)prm.chain_len;
 
-#define LOAD_RNG(R,slot) do { (R).col = rng_base + (slot); (R).a = st_a[slot]; (R).b = st_b[slot]; \
+#define LOAD_RNG(R,slot) do { (R).col = rng_base + (slot); (R).rcol = rsl_base + (slot); (R).a = st_a[slot]; (R).b = st_b[slot]; \
         (R).c = st_c[slot]; (R).cnt = (int)st_n[slot]; } while (0)
 #define STORE_RNG(R,slot) do { st_a[slot] = (R).a; st_b[slot] = (R).b; st_c[slot] = (R).c; \
         st_n[slot] = (u64)(R).cnt; } while (0)
@@ -415,6 +450,7 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel_regroup(const RenderP
         {
             Rng rng;
             rng.col = rng_base + tid;
+            rng.rcol = rsl_base + tid;
             rng.seed(splitmix64(prm.base_seed + prm.chain_first + kk));
 #pragma unroll
             for (int i = 0; i < D; ++i)
@@ -487,6 +523,7 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel_regroup(const RenderP
                     p[i] = sp[i*FFR_TPB + s];
                 Rng wr;
                 wr.col = rng_base + s;
+                wr.rcol = rsl_base + s;
                 const bool xr = (xf.flags & XF_USES_RNG) || (it >= 0 && has_final && (xfs[nx].flags & XF_USES_RNG));
                 if (xr)
                     LOAD_RNG(wr,s);
@@ -658,7 +695,7 @@ __global__ void __launch_bounds__(FFR_TPB,2) render_kernel_regroup(const RenderP
     }
 }
 
-#define FFR_SMEM_REGROUP_BYTES(D,RCAP) (FFR_SMEM_RNG_BYTES + 4*FFR_TPB*8 + (D)*FFR_TPB*8 + (RCAP)*FFR_TPB*8)
+#define FFR_SMEM_REGROUP_BYTES(D,RCAP) (16*FFR_TPB*8 + 4*FFR_TPB*8 + (D)*FFR_TPB*8 + (RCAP)*FFR_TPB*8)
 
 /* K2: dst += src with the reference's mixed element typing: element 0 of each cell is a u64
    count, elements 1..r are f64 colour sums (buffer_renderer.hpp:375-391). src may be peer
@@ -717,7 +754,7 @@ __global__ void __launch_bounds__(FFR_TPB) iterate_points_kernel(const DevFlame 
     if (i >= n)
         return;
     Rng rng;
-    rng.col = rng_base + threadIdx.x;
+    rng.bind(rng_base,threadIdx.x);
     rng.seed(seeds[i]);
     double p[D];
 #pragma unroll
@@ -734,7 +771,7 @@ __global__ void __launch_bounds__(FFR_TPB) isaac_words_kernel(u64 seed, u64 n, u
 {
     extern __shared__ __align__(16) unsigned char smem[];
     Rng rng;
-    rng.col = (u64*)smem + threadIdx.x;
+    rng.bind((u64*)smem,threadIdx.x);
     rng.seed(seed + threadIdx.x);
     if (threadIdx.x == 0)
         for (u64 i = 0; i < n; ++i)

@@ -307,6 +307,9 @@ int ffr_cuda_render_chains_async(ffr_ctx *ctx, uint64_t chain_first, uint64_t ch
         uint64_t chain_len, uint64_t last_len, uint64_t base_seed, uint64_t bv_limit);
 int ffr_cuda_sync(ffr_ctx *ctx);
 int ffr_cuda_get_stats(ffr_ctx *ctx, ffr_stats *stats);
+/* chains the render kernel keeps in flight per device (SMs x resident blocks x 256): size
+   chain counts as a multiple of this for full waves */
+uint64_t ffr_cuda_resident_chains(const ffr_ctx *ctx);
 /* number of kernel launches issued by this context so far */
 uint64_t ffr_cuda_launch_count(const ffr_ctx *ctx);
 

@@ -26,7 +26,7 @@ def main():
         fl = ffr.Flame(ex.example_json(ename, size=size))
         for mode, rg in [(m, g) for m in modes for g in regs]:
             r = ffr.BufferRenderer(fl, scatter_mode=mode, blocks_per_sm=bps, regroup=rg)
-            chains = 148 * 2 * 256 * waves
+            chains = r.resident_chains * waves
             r.render_chains(0, 148 * 2 * 256, 256)  # warm-up
             t0 = time.time()
             r.render_chains(0, chains, L, base_seed=5)

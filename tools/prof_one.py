@@ -11,5 +11,5 @@ ename, size = CONFIGS[nm]
 fl = ffr.Flame(ex.example_json(ename, size=size))
 r = ffr.BufferRenderer(fl, regroup=rg)
 r.render_chains(0, 148 * 2 * 256, 256)
-r.render_chains(0, 148 * 2 * 256 * waves, L, base_seed=5)
+r.render_chains(0, r.resident_chains * waves, L, base_seed=5)
 print(r.stats["s_iter"])
