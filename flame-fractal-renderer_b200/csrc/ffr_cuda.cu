@@ -29,7 +29,7 @@ uint32_t op_need(uint32_t op)
     case FFR_VAR_HORSESHOE: return R;
     case FFR_VAR_POLAR: return A|R;
     case FFR_VAR_POLAR2: return A|R2;
-    case FFR_VAR_HANDKERCHIEF: return A|R;
+    case FFR_VAR_HANDKERCHIEF: return SC; /* angle-sum form: needs y/r, x/r, not atan2 */
     case FFR_VAR_HEART: return A|R;
     case FFR_VAR_DISC: return A|R;
     case FFR_VAR_DISC2: return A;
@@ -38,7 +38,7 @@ uint32_t op_need(uint32_t op)
     case FFR_VAR_SPIRAL: return SC;
     case FFR_VAR_HYPERBOLIC: return SC;
     case FFR_VAR_DIAMOND: return SC;
-    case FFR_VAR_EX: return A|R;
+    case FFR_VAR_EX: return SC;
     case FFR_VAR_JULIA: return A|R;
     case FFR_VAR_POWER: return SC;
     case FFR_VAR_BLOB: return SC|A;
@@ -67,22 +67,6 @@ uint32_t op_need(uint32_t op)
     case FFR_VAR_ESCHER: return A|R2;
     case FFR_VAR_LOONIE: return R2;
     default: return 0;
-    }
-}
-
-bool op_uses_rng(uint32_t op)
-{
-    switch (op)
-    {
-    case FFR_VAR_NOISE: case FFR_VAR_BLUR: case FFR_VAR_GAUSSIAN_BLUR: case FFR_VAR_SQUARE_NOISE:
-    case FFR_VAR_PRE_BLUR: case FFR_VAR_JULIA: case FFR_VAR_JULIAN: case FFR_VAR_JULIASCOPE:
-    case FFR_VAR_RADIAL_BLUR: case FFR_VAR_PIE: case FFR_VAR_ARCH: case FFR_VAR_RAYS:
-    case FFR_VAR_BLADE: case FFR_VAR_TWINTRIAN: case FFR_VAR_WEDGE_JULIA: case FFR_VAR_SUPERSHAPE:
-    case FFR_VAR_FLOWER: case FFR_VAR_CONIC: case FFR_VAR_PARABOLA: case FFR_VAR_BOARDERS:
-    case FFR_VAR_CPOW:
-        return true;
-    default:
-        return false;
     }
 }
 
@@ -140,6 +124,7 @@ struct ffr_ctx
     uint32_t num_xforms = 0, num_ids = 0;
     bool has_final = false, affine_only = false, regroup = false;
     uint32_t distinct_oplists = 1;
+    double divergence_ratio = 1.0;
     std::vector<unsigned char> blob;
     std::vector<double> colors;
     std::vector<u64> json_ids;     /* sorted index -> JSON id */
@@ -338,13 +323,13 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
             dv.op = v.op;
             dv.axis_x = (d->dims == 2) ? 0 : v.axis_x;
             dv.axis_y = (d->dims == 2) ? 1 : v.axis_y;
-            dv.need = op_need(v.op);
+            dv.need = op_need(v.op) | (var_uses_rng(v.op) ? NEED_RNG : 0u);
             dv.weight = v.weight;
             memcpy(dv.p,v.params,sizeof(dv.p));
             dx.need |= dv.need;
             if (v.op != FFR_VAR_LINEAR)
                 affine_only = false;
-            if (op_uses_rng(v.op))
+            if (var_uses_rng(v.op))
             {
                 dx.flags |= XF_USES_RNG;
                 uses_rng = true;
@@ -365,6 +350,36 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
                 lists.push_back(l);
         }
         ctx->distinct_oplists = (uint32_t)lists.size();
+        /* Divergence model for choosing K1b. In K1 a warp executes, per position j of the
+           variation loop, every DISTINCT non-linear opcode its lanes hold there; in K1b a warp
+           runs one xform, i.e. the selection-weighted mean number of non-linear variations,
+           plus the per-iteration sort (~1.5 variation bodies). Measured: csci6360 (ratio 3.1)
+           gains 35 % from K1b, tkoz_test3 (1.8) loses 10 %. */
+        double direct = 0.0;
+        size_t maxlen = 0;
+        for (auto& l : lists) maxlen = std::max(maxlen,l.size());
+        for (size_t j = 0; j < maxlen; ++j)
+        {
+            std::vector<uint32_t> seen;
+            for (uint32_t i = 0; i < d->num_xforms; ++i)
+                if (j < xfs[i].var_count)
+                {
+                    uint32_t op = vars[xfs[i].var_begin + j].op;
+                    if (op != FFR_VAR_LINEAR && std::find(seen.begin(),seen.end(),op) == seen.end())
+                        seen.push_back(op);
+                }
+            direct += (double)seen.size();
+        }
+        double grouped = 1.5, prev = 0.0;
+        for (uint32_t i = 0; i < d->num_xforms; ++i)
+        {
+            uint32_t nl = 0;
+            for (uint32_t k = 0; k < xfs[i].var_count; ++k)
+                nl += vars[xfs[i].var_begin + k].op != FFR_VAR_LINEAR;
+            grouped += (d->xfcw[i] - prev) * nl;
+            prev = d->xfcw[i];
+        }
+        ctx->divergence_ratio = direct / grouped;
     }
     if (ctx->colors.empty())
         ctx->colors.push_back(0.0);
@@ -632,7 +647,8 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
     /* regroup (K1b) when lanes would otherwise diverge over different op lists */
     ctx->regroup = false;
     if (ctx->opt.regroup != 1 && ctx->r <= 4 && ctx->num_xforms <= 31 &&
-        ((ctx->opt.regroup == 2 && ctx->num_xforms >= 1) || (ctx->distinct_oplists >= 2)))
+        ((ctx->opt.regroup == 2 && ctx->num_xforms >= 1) ||
+         (ctx->distinct_oplists >= 2 && ctx->divergence_ratio > 2.2)))
     {
         size_t extra = 0;
         render_fn k = pick_regroup(ctx->dims,ctx->r,&extra);

@@ -44,6 +44,9 @@ struct RenderParams
 };
 
 #define FFR_SMEM_RNG_BYTES (FFR_RNG_WORDS*FFR_TPB*8)
+#ifndef FFR_DIRECT_MINB
+#define FFR_DIRECT_MINB 2
+#endif
 
 __device__ __forceinline__ void stage_blob(DevFlame *dst, const DevFlame *src, uint32_t bytes)
 {
@@ -93,7 +96,7 @@ __device__ __noinline__ ChainState<D,RCAP> chain_reinit(const DevFlame *fl, Rng 
 }
 
 template <int D, int RCAP, bool AFFINE_ONLY>
-__global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : 2) render_kernel(const RenderParams prm)
+__global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) render_kernel(const RenderParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned int s_group;
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : 2) render_kernel(con
    identical to K1 (and to the oracle). Needs num_xforms <= 31 and color_dims <= 4. */
 #define FFR_NWARPS (FFR_TPB/32)
 #ifndef FFR_REGROUP_MINB
-#define FFR_REGROUP_MINB 3
+#define FFR_REGROUP_MINB 2
 #endif
 
 template <int D, int RCAP>
