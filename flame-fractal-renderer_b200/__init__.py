@@ -91,6 +91,15 @@ class FfrOptions(C.Structure):
                 ("external_buffer", C.c_void_p), ("stream", C.c_void_p)]
 
 
+class FfrTonemapInfo(C.Structure):
+    _fields_ = [("hist_min", C.c_uint64), ("hist_max", C.c_uint64),
+                ("scaler_min", C.c_double), ("scaler_max", C.c_double),
+                ("width", C.c_uint32), ("height", C.c_uint32),
+                ("channels", C.c_uint32), ("bits", C.c_uint32)]
+
+
+TONE_MONO, TONE_GRAY, TONE_RGB = 1, 2, 3
+
 PROGRESS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_uint64)
 
 # every symbol include/ffr_cuda.h and include/ffr_flame.h declare: (restype, argtypes)
@@ -135,6 +144,8 @@ ABI = {
     "ffr_cuda_reduce": (C.c_int, [C.c_void_p]),
     "ffr_cuda_read_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ffr_cuda_histogram_sum_max": (C.c_int, [C.c_void_p, _u64p, _u64p]),
+    "ffr_cuda_tonemap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_size_t,
+                                   C.POINTER(FfrTonemapInfo)]),
     "ffr_cuda_iterate_points": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, _u64p, _f64p, _f64p]),
     "ffr_cuda_isaac_words": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, _u64p]),
     "ffr_cuda_atomic_roofline": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
@@ -343,6 +354,19 @@ class BufferRenderer:
         s, m = C.c_uint64(), C.c_uint64()
         self._check(lib().ffr_cuda_histogram_sum_max(self._h, C.byref(s), C.byref(m)))
         return s.value, m.value
+
+    def tonemap(self, mode, bits=8, gamma=1.0):
+        """ffr-img's pixel math on the device: returns (image ndarray [h, w(, 3)], info dict)."""
+        w, h = self.flame.size[0], self.flame.size[1]
+        ch = 3 if mode == TONE_RGB else 1
+        if mode == TONE_MONO:
+            bits = 8
+        img = np.empty((h, w, ch), dtype=np.uint8 if bits == 8 else np.uint16)
+        info = FfrTonemapInfo()
+        self._check(lib().ffr_cuda_tonemap(self._h, mode, bits, gamma, img.ctypes.data_as(C.c_void_p),
+                                           img.nbytes, C.byref(info)))
+        d = {k: getattr(info, k) for k, _ in FfrTonemapInfo._fields_}
+        return (img[:, :, 0] if ch == 1 else img), d
 
     def iterate_points(self, xf_index, seeds, pts):
         pts = np.ascontiguousarray(pts, dtype=np.float64)

@@ -119,6 +119,7 @@ typedef void (*render_fn)(const RenderParams);
 struct ffr_ctx
 {
     uint32_t dims = 0, r = 0, cellsz = 1;
+    uint32_t size0 = 1, size1 = 1;
     u64 cells = 0;
     size_t bytes = 0;
     uint32_t num_xforms = 0, num_ids = 0;
@@ -400,6 +401,8 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
     if (!vars.empty())
         memcpy(ctx->blob.data()+hdr.var_off,vars.data(),vars.size()*sizeof(DevVar));
     ctx->dims = d->dims;
+    ctx->size0 = (uint32_t)d->size[0];
+    ctx->size1 = d->dims > 1 ? (uint32_t)d->size[1] : 1;
     ctx->r = d->color_dims;
     ctx->cellsz = hdr.cell;
     ctx->cells = cells;
@@ -1005,6 +1008,98 @@ int ffr_cuda_histogram_sum_max(ffr_ctx *ctx, uint64_t *sum, uint64_t *max)
     CK(cudaStreamSynchronize(ds.stream));
     if (sum) *sum = h[0];
     if (max) *max = h[1];
+    return FFR_OK;
+}
+
+int ffr_cuda_tonemap(ffr_ctx *ctx, int mode, int bits, double gamma, void *pixels, size_t bytes,
+        ffr_tonemap_info *info)
+{
+    if (!ctx || !pixels)
+        return FFR_E_INVALID;
+    if (ctx->dims != 2)
+    {
+        ctx->err = "only 2D flames supported"; /* ffr_img.cpp:123-127 */
+        return FFR_E_INVALID;
+    }
+    if (!(gamma >= 1e-20)) /* ffr_img.cpp:88-89 */
+    {
+        ctx->err = "gamma too small";
+        return FFR_E_INVALID;
+    }
+    if (bits != 8 && bits != 16) /* :94-95 */
+    {
+        ctx->err = "bits per channel must be 8 or 16";
+        return FFR_E_INVALID;
+    }
+    if (mode != FFR_TONE_MONO && mode != FFR_TONE_GRAY && mode != FFR_TONE_RGB)
+    {
+        ctx->err = "no coloring flag";
+        return FFR_E_INVALID;
+    }
+    if (mode == FFR_TONE_RGB && ctx->r != 3) /* :282-283 */
+    {
+        ctx->err = "buffer must use 3 color dimensions";
+        return FFR_E_INVALID;
+    }
+    if (mode == FFR_TONE_MONO)
+        bits = 8; /* renderGrayImage<u8>, :264 */
+    const uint32_t channels = (mode == FFR_TONE_RGB) ? 3 : 1;
+    const size_t need = (size_t)ctx->cells*channels*(bits/8);
+    if (bytes != need)
+    {
+        ctx->err = "tonemap: pixel buffer size mismatch";
+        return FFR_E_INVALID;
+    }
+    int rc = ffr_cuda_reduce(ctx);
+    if (rc != FFR_OK)
+        return rc;
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    const u64 init[2] = {~0ULL,0ULL};
+    CK(cudaMemcpyAsync(ds.d_scratch,init,sizeof(init),cudaMemcpyHostToDevice,ds.stream));
+    unsigned grid = (unsigned)std::min<u64>((ctx->cells + 255)/256,(u64)ds.sm_count*16);
+    hist_min_max_kernel<<<grid,256,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,ds.d_scratch,
+        ds.d_scratch+1);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    u64 mm[2];
+    CK(cudaMemcpyAsync(mm,ds.d_scratch,sizeof(mm),cudaMemcpyDeviceToHost,ds.stream));
+    CK(cudaStreamSynchronize(ds.stream));
+    if (info)
+    {
+        memset(info,0,sizeof(*info));
+        info->hist_min = mm[0];
+        info->hist_max = mm[1];
+        info->scaler_min = log(1 + (double)mm[0]);
+        info->scaler_max = log(1 + (double)mm[1]);
+        info->width = ctx->size0;
+        info->height = ctx->size1;
+        info->channels = channels;
+        info->bits = (uint32_t)bits;
+    }
+    if (log(1 + (double)mm[1]) < 1e-20) /* :231-232 */
+    {
+        ctx->err = "histogram is (probably) empty";
+        return FFR_E_INVALID;
+    }
+    void *d_pix = nullptr;
+    CK(cudaMalloc(&d_pix,need));
+    const double gp = 1.0 / gamma; /* :235 */
+    if (bits == 8)
+        tonemap_kernel<unsigned char><<<grid,256,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,mode,
+            mm[1],gp,(unsigned char*)d_pix);
+    else
+        tonemap_kernel<unsigned short><<<grid,256,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,mode,
+            mm[1],gp,(unsigned short*)d_pix);
+    ++ctx->launches;
+    if (!cuda_ok(ctx,cudaGetLastError(),"tonemap_kernel") ||
+        !cuda_ok(ctx,cudaMemcpyAsync(pixels,d_pix,need,cudaMemcpyDeviceToHost,ds.stream),"tonemap D2H") ||
+        !cuda_ok(ctx,cudaStreamSynchronize(ds.stream),"tonemap sync"))
+    {
+        cudaFree(d_pix);
+        return FFR_E_CUDA;
+    }
+    cudaFree(d_pix);
     return FFR_OK;
 }
 

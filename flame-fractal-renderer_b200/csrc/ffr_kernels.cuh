@@ -744,6 +744,83 @@ __global__ void hist_sum_max_kernel(const u64 *__restrict__ buf, u64 cells, uint
     }
 }
 
+/* K4a: histogram min/max for the tone map (ImageRenderer::getValueBounds,
+   image_renderer.hpp:112-127, with func = count) */
+__global__ void hist_min_max_kernel(const u64 *__restrict__ buf, u64 cells, uint32_t cellsz,
+        u64 *out_min, u64 *out_max)
+{
+    u64 mn = ~0ULL, mx = 0;
+    const u64 stride = (u64)gridDim.x*blockDim.x;
+    for (u64 i = (u64)blockIdx.x*blockDim.x + threadIdx.x; i < cells; i += stride)
+    {
+        const u64 v = buf[i*cellsz];
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        const u64 a = __shfl_xor_sync(0xffffffffu,mn,o);
+        const u64 b = __shfl_xor_sync(0xffffffffu,mx,o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicMin(out_min,mn);
+        atomicMax(out_max,mx);
+    }
+}
+
+/* K4b: log-density tone map, one thread per cell, coalesced: reads (1+r)*8 B, writes
+   channels*bits/8 B per cell (HBM bound). Pixel math of render_image, src/ffr_img.cpp:
+     gray  l = log(1+n)/max; v = pow(l,1/gamma); pix = (pix_t)(v*pix_scale)      :236-243
+     rgb   v * colour_i/n per channel                                            :283-294
+     mono  n != 0 ? 1 : 0                                                        :259-263
+   pix_scale = 2^bits * (1 - 2^-52) (constants.hpp:77-91). `max` = log(1 + hist_max) evaluated
+   with the SAME device log as the cells so the brightest cell maps to exactly 1.0 as in the
+   reference (log is monotonic, so this equals the max over cells of log(1+n)). Cells with
+   n == 0 in RGB mode are NaN in the reference (0/0, then an undefined cast that yields 0 on
+   x86-64): they are 0 here. Values are clamped to the top code instead of wrapping. */
+template <typename PIX>
+__global__ void tonemap_kernel(const u64 *__restrict__ buf, u64 cells, uint32_t cellsz, int mode,
+        u64 hist_max, double gp, PIX *__restrict__ out)
+{
+    const double pix_scale = (double)(1ULL << (8*sizeof(PIX))) * (1.0 - 1.0/4503599627370496.0);
+    const double top = (double)((1ULL << (8*sizeof(PIX))) - 1);
+    const double mx = log(1 + (double)hist_max);
+    const u64 stride = (u64)gridDim.x*blockDim.x;
+    for (u64 i = (u64)blockIdx.x*blockDim.x + threadIdx.x; i < cells; i += stride)
+    {
+        const u64 *cell = buf + i*cellsz;
+        const u64 n = cell[0];
+        if (mode == FFR_TONE_MONO)
+        {
+            out[i] = (PIX)((n != 0 ? 1.0 : 0.0) * pix_scale);
+            continue;
+        }
+        const double l = log(1 + (double)n) / mx;
+        const double ll = pow(l,gp);
+        if (mode == FFR_TONE_GRAY)
+        {
+            const double v = ll * pix_scale;
+            out[i] = (PIX)(v > top ? top : v);
+        }
+        else
+        {
+            const double h = (double)n;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+            {
+                double v = (n == 0) ? 0.0
+                    : (ll * (__longlong_as_double((long long)cell[1+c]) / h)) * pix_scale;
+                v = v > top ? top : (v < 0.0 ? 0.0 : v);
+                out[i*3+c] = (PIX)v;
+            }
+        }
+    }
+}
+
 /* T1: one XForm::applyIteration per point with its own seeded stream */
 template <int D>
 __global__ void __launch_bounds__(FFR_TPB) iterate_points_kernel(const DevFlame *blob,

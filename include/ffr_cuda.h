@@ -324,6 +324,31 @@ int ffr_cuda_read_buffer(ffr_ctx *ctx, void *host, size_t bytes);
 /* histogramSum / histogramMax (buffer_renderer.hpp:483-509) computed on the device */
 int ffr_cuda_histogram_sum_max(ffr_ctx *ctx, uint64_t *sum, uint64_t *max);
 
+/* ---- log-density tone map: the pixel math of ffr-img (src/ffr_img.cpp:199-309,
+   renderers/image_renderer.hpp:112-192), 2-d flames only ---- */
+enum ffr_tonemap_mode
+{
+    FFR_TONE_MONO = 1,   /* -m: count != 0 ? 1 : 0, 8-bit gray            ffr_img.cpp:259-265 */
+    FFR_TONE_GRAY = 2,   /* -g: pow(log(1+n)/max, 1/gamma)                :236-243,267-279 */
+    FFR_TONE_RGB  = 3    /* -c: that times colour_i/n, 3 colour dims only :280-305 */
+};
+
+typedef struct ffr_tonemap_info
+{
+    uint64_t hist_min, hist_max;     /* "histogram bounds" line, ffr_img.cpp:217-218 */
+    double scaler_min, scaler_max;   /* "scaler bounds" line: log(1+n) extremes, :229-230 */
+    uint32_t width, height, channels, bits;
+} ffr_tonemap_info;
+
+/* Sums the device buffers (like ffr_cuda_read_buffer), reduces min/max, maps every cell to a
+   pixel on the device and copies the image to `pixels`: height rows of width pixels, row y =
+   buffer dimension 1, `channels` samples per pixel, samples of `bits` (8 or 16) bits in HOST
+   byte order. bytes must be width*height*channels*bits/8. Errors follow ffr-img: "gamma too
+   small" (< 1e-20), "bits per channel must be 8 or 16", "buffer must use 3 color dimensions",
+   "only 2D flames supported", "histogram is (probably) empty". */
+int ffr_cuda_tonemap(ffr_ctx *ctx, int mode, int bits, double gamma, void *pixels, size_t bytes,
+        ffr_tonemap_info *info);
+
 /* Test hook on the same device code as the render kernels: for each of n points, seed
    an ISAAC stream with seeds[i] (Isaac::setSeed(u64)) and apply xform #xf_index (sorted
    order; -1 = final xform) once: XForm::applyIteration (types/xform.hpp:211-227).

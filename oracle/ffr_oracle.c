@@ -1666,3 +1666,77 @@ int oracle_iterate_points(const ffr_flame_desc *fl, int64_t xf_index, u64 n, con
     }
     return 0;
 }
+
+/* ---------------- tone map ----------------
+   Restates render_image (src/ffr_img.cpp:199-309) + ImageRenderer::getValueBounds /
+   renderGrayImage / renderColorImageRGB (renderers/image_renderer.hpp:112-192) for one pixel
+   format. PARITY UNPINNED for this function: ffr-img cannot be built here (boost::gil and
+   libpng headers are absent), so there is no reference output to pin it to; the arithmetic is
+   a dozen lines and is restated literally. mode: 1 mono, 2 gray, 3 rgb; bits 8 or 16; out is
+   u8 or u16 samples, channels interleaved. Returns 0, or -1 "histogram is (probably) empty".
+   The double -> pixel casts of NaN (rgb, count 0: 0/0) and of 2^bits are undefined in the
+   reference; as on the device they yield 0 and the top code. */
+int oracle_tonemap(const u64 *buf, u64 cells, uint32_t cellsz, int mode, int bits, double gamma,
+        void *out, u64 *hist_min, u64 *hist_max, double *sc_min, double *sc_max)
+{
+    /* pix_scale_v<pix_t,double>, constants.hpp:77-91 */
+    const double scale_adjust_down = 1.0 - (double)(float)(1.0 / (double)(1L << 52));
+    const double pix_scale = (bits == 8 ? 256.0 : 65536.0) * scale_adjust_down;
+    const double top = bits == 8 ? 255.0 : 65535.0;
+    u64 minh = buf[0], maxh = buf[0];
+    double mn = log(1 + (double)buf[0]), mx = mn;
+    for (u64 i = 0; i < cells; ++i) /* getValueBounds :116-126 with funch and func1 */
+    {
+        u64 n = buf[i*cellsz];
+        double l = log(1 + (double)n);
+        if (n < minh) minh = n;
+        if (n > maxh) maxh = n;
+        if (l < mn) mn = l;
+        if (l > mx) mx = l;
+    }
+    if (hist_min) *hist_min = minh;
+    if (hist_max) *hist_max = maxh;
+    if (sc_min) *sc_min = mn;
+    if (sc_max) *sc_max = mx;
+    if (mx < EPS) /* :231-232 */
+        return -1;
+    double gp = 1.0 / gamma; /* :235 */
+    for (u64 i = 0; i < cells; ++i)
+    {
+        const u64 *cell = buf + i*cellsz;
+        u64 n = cell[0];
+        double vals[3];
+        int ch = 1;
+        if (mode == 1) /* :259-263 */
+            vals[0] = n != 0 ? 1.0 : 0.0;
+        else
+        {
+            double l = log(1 + (double)n) / mx; /* :240-241 */
+            double ll = pow(l,gp);
+            if (mode == 2)
+                vals[0] = ll;
+            else /* :284-294 */
+            {
+                double h = (double)n;
+                ch = 3;
+                for (int c = 0; c < 3; ++c)
+                {
+                    double col;
+                    memcpy(&col,&cell[1+c],8);
+                    vals[c] = ll*(col / h);
+                }
+            }
+        }
+        for (int c = 0; c < ch; ++c)
+        {
+            double v = vals[c] * pix_scale; /* image_renderer.hpp:162,185-187 */
+            if (isnan(v) || v < 0.0) v = 0.0;
+            if (v > top) v = top;
+            if (bits == 8 || mode == 1)
+                ((uint8_t*)out)[i*ch+c] = (uint8_t)v;
+            else
+                ((uint16_t*)out)[i*ch+c] = (uint16_t)v;
+        }
+    }
+    return 0;
+}

@@ -44,6 +44,9 @@ def oracle():
         l.oracle_render_chains.argtypes = [C.POINTER(ffr.FfrFlameDesc)] + [C.c_uint64] * 6 + [
             C.c_void_p, C.POINTER(ffr.FfrStats), C.c_int]
         l.oracle_set_nan_emulation.argtypes = [C.c_int]
+        l.oracle_tonemap.restype = C.c_int
+        l.oracle_tonemap.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double,
+                                     C.c_void_p, _u64p, _u64p, _f64p, _f64p]
         l.oracle_iterate_points.restype = C.c_int
         l.oracle_iterate_points.argtypes = [C.POINTER(ffr.FfrFlameDesc), C.c_int64, C.c_uint64,
                                             _u64p, _f64p, _f64p]
@@ -128,6 +131,25 @@ def oracle_iterate_points(flame, xf_index, seeds, pts):
     if rc:
         raise RuntimeError("oracle_iterate_points failed")
     return out
+
+
+def oracle_tonemap(raw, width, height, color_dims, mode, bits=8, gamma=1.0):
+    """ffr-img pixel math on the CPU: returns (image, info dict)."""
+    raw = np.ascontiguousarray(raw).view(np.uint64)
+    ch = 3 if mode == 3 else 1
+    if mode == 1:
+        bits = 8
+    img = np.zeros((height, width, ch), dtype=np.uint8 if bits == 8 else np.uint16)
+    hmin, hmax = C.c_uint64(), C.c_uint64()
+    smin, smax = C.c_double(), C.c_double()
+    rc = oracle().oracle_tonemap(raw.ctypes.data_as(C.c_void_p), width * height, 1 + color_dims,
+                                 mode, bits, gamma, img.ctypes.data_as(C.c_void_p),
+                                 C.byref(hmin), C.byref(hmax), C.byref(smin), C.byref(smax))
+    if rc:
+        raise RuntimeError("histogram is (probably) empty")
+    info = {"hist_min": hmin.value, "hist_max": hmax.value, "scaler_min": smin.value,
+            "scaler_max": smax.value}
+    return (img[:, :, 0] if ch == 1 else img), info
 
 
 def oracle_isaac_words(seed, n):

@@ -98,3 +98,25 @@ def test_threaded_oracle_counts_are_exact(ffr, po, examples):
     np.testing.assert_allclose(cola, colb, rtol=1e-12, atol=1e-12)
     for k in ("s_iter", "s_plot", "xf_dist", "pt_min", "pt_max"):
         assert sa[k] == sb[k]
+
+
+def test_oracle_tonemap_properties(ffr, po, examples):
+    """ffr-img pixel math (oracle restatement; unpinned, see ffr_oracle.c): exact identities
+    that follow from src/ffr_img.cpp:236-243 -- the brightest cell is the top code, empty cells
+    are 0, gamma 1 grey equals floor(log(1+n)/log(1+max) * 256(1-2^-52)), output is monotone
+    in the count."""
+    fl = ffr.Flame(examples.example_json("barnsley_fern", size=[96, 64]))
+    raw, st, _ = po.oracle_render(fl, 40, 2000, base_seed=2)
+    counts = raw.reshape(64, 96)
+    for bits, top in ((8, 255), (16, 65535)):
+        img, info = po.oracle_tonemap(raw, 96, 64, 0, 2, bits=bits, gamma=1.0)
+        assert info["hist_max"] == counts.max() and info["hist_min"] == counts.min()
+        assert img[counts == counts.max()].min() == top
+        assert (img[counts == 0] == 0).all()
+        scale = (top + 1) * (1.0 - 2.0 ** -52)
+        want = np.floor(np.log(1.0 + counts.astype(np.float64)) / info["scaler_max"] * scale)
+        assert np.array_equal(img, np.minimum(want, top).astype(img.dtype))
+        order = np.argsort(counts.ravel(), kind="stable")
+        assert (np.diff(img.ravel()[order].astype(np.int64)) >= 0).all()
+    mono, _ = po.oracle_tonemap(raw, 96, 64, 0, 1)
+    assert np.array_equal(mono, np.where(counts != 0, 255, 0).astype(np.uint8))
