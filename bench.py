@@ -53,6 +53,14 @@ METRIC = "chaos-game samples/sec into buffer"
 UNIT = "samples/s"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per PLOTTED sample of the render kernel, from the
+# committed `ncu --set full` captures (profiles/README.md); traffic per launch = this x plotted
+NCU_DRAM_BYTES_PER_PLOTTED = {
+    "csci6360_4096": (0.2489e9 + 2.2624e9) / 492.7e6,   # profiles/r1_render_regroup_csci4096
+    "sierpinski3d_512": (8.46e6 + 0.535e6) / 620.8e6,   # profiles/r1_render_affine_sierp3d
+}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -370,7 +378,9 @@ def main():
                     "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None,
+                         "frac": achieved / hbm_peak,
+                         "traffic": (NCU_DRAM_BYTES_PER_PLOTTED[wl_name] * plotted / args.steps
+                                     if wl_name in NCU_DRAM_BYTES_PER_PLOTTED else None),
                          "peak_source": peak_src, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "plotted_fraction": plotted / iterated,
