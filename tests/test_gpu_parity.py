@@ -258,3 +258,43 @@ def test_statistical_parity(ffr, po, examples, name, size):
         cfloor = max(cdist(oruns[i], oruns[j]) for i, j in pairs)
         cworst = max(cdist(g, o) for g in gruns for o in oruns)
         assert cworst <= 1.5 * cfloor + 1e-3, (cworst, cfloor)
+
+
+def _ulps(a, b):
+    """distance in units of the last place of b"""
+    return np.abs(a - b) / np.spacing(np.abs(b))
+
+
+def test_device_sin_cos_accuracy(ffr):
+    """Device sin/cos (out-of-line libdevice wrappers, ffr_device.cuh) against glibc through
+    flames that expose the functions directly: sinusoidal gives sin(x); pdj with a=0,b=1,c=1,d=0 gives
+    (-cos(x), sin(x) - 1). Stated tolerance: <= 2 ULP of the result (libdevice is
+    documented at 1-2 ULP), for |x| on both sides of libdevice's 105615 switch to Payne-Hanek."""
+    import json
+    ident = {"A": [[1, 0], [0, 1]], "b": [0, 0]}
+    def flame(var):
+        return json.dumps({"dimensions": 2, "size": [8, 8], "bounds": [[-1, 1], [-1, 1]],
+                           "xforms": [{"weight": 1, "variations": [var], "pre_affine": ident}]})
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([rng.uniform(-4, 4, 20000), rng.uniform(-1e3, 1e3, 20000),
+                         rng.uniform(-1.05e5, 1.05e5, 20000), rng.uniform(-1e9, 1e9, 5000),
+                         np.array([0.0, -0.0, np.pi / 4, -np.pi / 4, np.pi / 2, 1e-300, 105614.9, 105615.1]),
+                         np.pi / 2 * np.arange(-2000, 2000) + rng.uniform(-1e-9, 1e-9, 4000)])
+    pts = np.stack([xs, xs[::-1]], axis=1)
+    seeds = np.zeros(len(xs), dtype=np.uint64)
+    r = ffr.BufferRenderer(ffr.Flame(flame({"name": "sinusoidal", "weight": 1.0})))
+    got = r.iterate_points(0, seeds, pts)
+    r.close()
+    want = np.sin(pts)
+    big = np.abs(want) > 1e-12   # near a zero of sin the absolute error is bounded by ulp(x) instead
+    assert _ulps(got[big], want[big]).max() <= 2.0
+    assert np.abs(got - want)[~big].max() <= 4e-12
+    r = ffr.BufferRenderer(ffr.Flame(flame({"name": "pdj", "weight": 1.0, "a": 0.0, "b": 1.0, "c": 1.0, "d": 0.0})))
+    got = r.iterate_points(0, seeds, pts)
+    r.close()
+    wc = -np.cos(xs)
+    bigc = np.abs(wc) > 1e-12
+    assert _ulps(got[bigc, 0], wc[bigc]).max() <= 2.0
+    assert np.abs(got[:, 0] - wc)[~bigc].max() <= 4e-12
+    ws = np.sin(xs) - 1.0
+    assert np.abs(got[:, 1] - ws).max() <= 4e-16 * 2
