@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--waves", type=int, default=2,
+    ap.add_argument("--waves", type=int, default=4,
                     help="chain groups per resident block and step")
     ap.add_argument("--ref-samples", type=int, default=20_000_000,
                     help="bounded CPU sample per step for the reference arm / cpu_baseline")

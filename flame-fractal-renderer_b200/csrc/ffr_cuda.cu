@@ -107,6 +107,8 @@ struct DeviceState
     unsigned int *d_counter = nullptr;
     u64 *d_scratch = nullptr;      /* 2 x u64 for histogram sum/max */
     u64 *d_rsl = nullptr;          /* K1b randrsl scratch */
+    u64 *d_stage = nullptr;        /* staging for add_buffer, kept between calls */
+    size_t stage_elems = 0;
     int sm_count = 0;
     int blocks_per_sm = 0;
     bool dirty = false;            /* holds samples not yet reduced into device 0 */
@@ -693,6 +695,7 @@ void ffr_cuda_destroy(ffr_ctx *ctx)
         if (ds.d_counter) cudaFree(ds.d_counter);
         if (ds.d_scratch) cudaFree(ds.d_scratch);
         if (ds.d_rsl) cudaFree(ds.d_rsl);
+        if (ds.d_stage) cudaFree(ds.d_stage);
         if (ds.own_stream && ds.stream) cudaStreamDestroy(ds.stream);
     }
     delete ctx;
@@ -731,30 +734,33 @@ int ffr_cuda_add_buffer(ffr_ctx *ctx, const void *host, size_t bytes)
     }
     DeviceState &ds = ctx->devs[0];
     CK(cudaSetDevice(ds.dev));
-    /* stage in chunks so a 1 GiB -i file does not double the footprint */
-    const size_t chunk_elems = (size_t)1 << 24; /* 128 MiB, multiple of any cell size handled below */
+    /* stage in chunks so a 1 GiB -i file does not double the footprint; the staging buffer
+       is kept for the next call */
+    const size_t chunk_elems = (size_t)1 << 24; /* 128 MiB */
     const size_t n_elems = bytes/8;
     size_t chunk = std::min(n_elems,chunk_elems - (chunk_elems % ctx->cellsz));
-    u64 *tmp = nullptr;
-    CK(cudaMalloc(&tmp,chunk*8));
-    int rc = FFR_OK;
-    for (size_t off = 0; off < n_elems && rc == FFR_OK; off += chunk)
+    if (ds.stage_elems < chunk)
+    {
+        if (ds.d_stage)
+            cudaFree(ds.d_stage);
+        ds.d_stage = nullptr;
+        ds.stage_elems = 0;
+        CK(cudaMalloc(&ds.d_stage,chunk*8));
+        ds.stage_elems = chunk;
+    }
+    u64 *tmp = ds.d_stage;
+    for (size_t off = 0; off < n_elems; off += chunk)
     {
         size_t n = std::min(chunk,n_elems - off);
-        if (!cuda_ok(ctx,cudaMemcpyAsync(tmp,(const u64*)host + off,n*8,cudaMemcpyHostToDevice,ds.stream),
-                "cudaMemcpyAsync(add_buffer)"))
-        {
-            rc = FFR_E_CUDA;
-            break;
-        }
+        CK(cudaMemcpyAsync(tmp,(const u64*)host + off,n*8,cudaMemcpyHostToDevice,ds.stream));
         unsigned grid = (unsigned)std::min<size_t>((n + 255)/256,(size_t)ds.sm_count*16);
         add_buffer_kernel<<<grid,256,0,ds.stream>>>(ds.buffer + off,tmp,n,ctx->cellsz);
         ++ctx->launches;
-        if (!cuda_ok(ctx,cudaStreamSynchronize(ds.stream),"add_buffer_kernel"))
-            rc = FFR_E_CUDA;
+        CK(cudaGetLastError());
+        /* the staging buffer is reused by the next chunk and the host buffer is only borrowed */
+        CK(cudaStreamSynchronize(ds.stream));
     }
-    cudaFree(tmp);
-    return rc;
+    return FFR_OK;
 }
 
 int ffr_cuda_clear_buffer(ffr_ctx *ctx)
