@@ -286,11 +286,13 @@ def main():
     alg_bytes = plotted / args.steps * 2 * (1 + r_dims) * 8
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
 
-    # measured random-atomic (uniform cells) roofline on the same buffer shape
-    atomic_ms = rend.atomic_roofline(1 << 28)  # warm
-    n_at = 1 << 30
-    atomic_ms = rend.atomic_roofline(n_at)
+    # measured atomic-scatter rooflines on the same buffer: uniformly random cells,
+    # and a replay of this flame's own attractor trace (same warps, same hot-cell collisions)
+    rend.atomic_roofline(1 << 28)  # warm
+    atomic_ms, n_at = rend.atomic_roofline(1 << 30)
     atomics_per_s = n_at / (atomic_ms * 1e-3)
+    replay_ms, n_rp = rend.atomic_roofline(1 << 28, pattern=1)
+    replay_per_s = n_rp / (replay_ms * 1e-3)
     buf.zero_()
 
     # ---- e2e through the C ABI with host buffers ----
@@ -386,8 +388,10 @@ def main():
                          "plotted_fraction": plotted / iterated,
                          "note": "fp64-issue bound on this flame, not HBM bound: see DESIGN.md"},
             "atomic_roofline": {"uniform_random_cells_per_s": atomics_per_s,
+                                "attractor_replay_cells_per_s": replay_per_s,
                                 "plotted_samples_per_s": plotted / args.steps / (k_ms * 1e-3),
-                                "frac": (plotted / args.steps / (k_ms * 1e-3)) / atomics_per_s},
+                                "frac": (plotted / args.steps / (k_ms * 1e-3)) / atomics_per_s,
+                                "frac_of_replay": (plotted / args.steps / (k_ms * 1e-3)) / replay_per_s},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

@@ -43,7 +43,7 @@ FFR_E_CUDA = -2
 FFR_E_NODEVICE = -3
 FFR_E_UNSUPPORTED = -4
 
-SCATTER_AUTO, SCATTER_GLOBAL, SCATTER_WARP_AGG, SCATTER_SMEM_TILE = 0, 1, 2, 3
+SCATTER_AUTO, SCATTER_GLOBAL, SCATTER_WARP_AGG, SCATTER_SMEM_TILE, SCATTER_DISCARD = 0, 1, 2, 3, 4
 
 
 class FfrVariation(C.Structure):
@@ -149,6 +149,8 @@ ABI = {
     "ffr_cuda_iterate_points": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, _u64p, _f64p, _f64p]),
     "ffr_cuda_isaac_words": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, _u64p]),
     "ffr_cuda_atomic_roofline": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
+    "ffr_cuda_atomic_roofline_ex": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float),
+                                              _u64p]),
 }
 
 _lib = None
@@ -383,9 +385,12 @@ class BufferRenderer:
         return out
 
     def atomic_roofline(self, n_atomics, pattern=0):
+        """(milliseconds, cells hit): pattern 0 uniform random cells, 1 attractor replay."""
         ms = C.c_float()
-        self._check(lib().ffr_cuda_atomic_roofline(self._h, n_atomics, pattern, C.byref(ms)))
-        return ms.value
+        n = C.c_uint64()
+        self._check(lib().ffr_cuda_atomic_roofline_ex(self._h, n_atomics, pattern, C.byref(ms),
+                                                      C.byref(n)))
+        return ms.value, n.value
 
 
 def split_counts_colors(raw, cells, color_dims):

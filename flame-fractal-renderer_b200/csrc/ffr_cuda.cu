@@ -107,6 +107,7 @@ struct DeviceState
     unsigned int *d_counter = nullptr;
     u64 *d_scratch = nullptr;      /* 2 x u64 for histogram sum/max */
     u64 *d_rsl = nullptr;          /* K1b randrsl scratch */
+    u64 *d_trace = nullptr;        /* only while ffr_cuda_atomic_roofline records a trace */
     u64 *d_stage = nullptr;        /* staging for add_buffer, kept between calls */
     size_t stage_elems = 0;
     int sm_count = 0;
@@ -499,6 +500,7 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
     prm.stats = ds.d_stats;
     prm.work_counter = ds.d_counter;
     prm.rsl_scratch = ds.d_rsl;
+    prm.trace = ds.d_trace;
     prm.chain_first = chain_first;
     prm.chain_count = chain_count;
     prm.chain_len = chain_len;
@@ -507,6 +509,11 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
     prm.bv_limit = bv_limit;
     prm.blob_bytes = (uint32_t)ctx->blob.size();
     prm.scatter_mode = ctx->scatter_mode;
+    if (chain_len >= (1ULL << 31) - 64)
+    {
+        ctx->err = "chain length (batch size) must be below 2^31 on the device path";
+        return FFR_E_INVALID;
+    }
     const u64 groups = (chain_count + FFR_TPB - 1) / FFR_TPB;
     if (groups > 0xfffffff0ULL)
     {
@@ -1199,12 +1206,18 @@ int ffr_cuda_isaac_words(ffr_ctx *ctx, uint64_t seed, uint64_t n, uint64_t *out)
 
 int ffr_cuda_atomic_roofline(ffr_ctx *ctx, uint64_t n_atomics, int pattern, float *ms)
 {
+    return ffr_cuda_atomic_roofline_ex(ctx,n_atomics,pattern,ms,nullptr);
+}
+
+int ffr_cuda_atomic_roofline_ex(ffr_ctx *ctx, uint64_t n_atomics, int pattern, float *ms,
+        uint64_t *n_done)
+{
     if (!ctx || !ms)
         return FFR_E_INVALID;
-    if (pattern != 0)
+    if (pattern != 0 && pattern != 1)
     {
-        ctx->err = "atomic_roofline: only pattern 0 (uniform cells) is implemented";
-        return FFR_E_UNSUPPORTED;
+        ctx->err = "atomic_roofline: pattern must be 0 (uniform cells) or 1 (attractor replay)";
+        return FFR_E_INVALID;
     }
     DeviceState &ds = ctx->devs[0];
     CK(cudaSetDevice(ds.dev));
@@ -1214,18 +1227,61 @@ int ffr_cuda_atomic_roofline(ffr_ctx *ctx, uint64_t n_atomics, int pattern, floa
     cudaEvent_t e0,e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0,ds.stream));
-    atomic_bench_kernel<<<(unsigned)grid,FFR_TPB,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,per_thread,
-        0x1234u + ctx->launches);
-    ++ctx->launches;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(e1,ds.stream));
-    CK(cudaEventSynchronize(e1));
-    CK(cudaEventElapsedTime(ms,e0,e1));
+    int rc = FFR_OK;
+    if (pattern == 0)
+    {
+        CK(cudaEventRecord(e0,ds.stream));
+        atomic_bench_kernel<<<(unsigned)grid,FFR_TPB,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,
+            per_thread,0x1234u + ctx->launches);
+        ++ctx->launches;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1,ds.stream));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(ms,e0,e1));
+        if (n_done)
+            *n_done = per_thread*threads;
+    }
+    else
+    {
+        /* record: one full wave of chains, per_thread samples each, statistics saved/restored */
+        u64 *trace = nullptr;
+        DevStats *saved = nullptr;
+        CK(cudaMalloc(&trace,threads*per_thread*sizeof(u64)));
+        CK(cudaMalloc(&saved,sizeof(DevStats)));
+        CK(cudaMemsetAsync(trace,0xff,threads*per_thread*sizeof(u64),ds.stream));
+        CK(cudaMemcpyAsync(saved,ds.d_stats,sizeof(DevStats),cudaMemcpyDeviceToDevice,ds.stream));
+        const uint32_t mode = ctx->scatter_mode;
+        ctx->scatter_mode = FFR_SCATTER_TRACE;
+        ds.d_trace = trace;
+        rc = launch_render(ctx,ds,0x7ace0000ULL,threads,per_thread,0,1,~0ULL);
+        ctx->scatter_mode = mode;
+        ds.d_trace = nullptr;
+        if (rc == FFR_OK)
+        {
+            DevStats after;
+            CK(cudaMemcpyAsync(&after,ds.d_stats,sizeof(DevStats),cudaMemcpyDeviceToHost,ds.stream));
+            DevStats before;
+            CK(cudaMemcpyAsync(&before,saved,sizeof(DevStats),cudaMemcpyDeviceToHost,ds.stream));
+            CK(cudaStreamSynchronize(ds.stream));
+            if (n_done)
+                *n_done = after.s_plot - before.s_plot;
+            CK(cudaMemcpyAsync(ds.d_stats,saved,sizeof(DevStats),cudaMemcpyDeviceToDevice,ds.stream));
+            CK(cudaEventRecord(e0,ds.stream));
+            atomic_replay_kernel<<<(unsigned)grid,FFR_TPB,0,ds.stream>>>(ds.buffer,trace,threads,per_thread,
+                ctx->cellsz);
+            ++ctx->launches;
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e1,ds.stream));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(ms,e0,e1));
+        }
+        cudaFree(trace);
+        cudaFree(saved);
+    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     ds.dirty = true;
-    return FFR_OK;
+    return rc;
 }
 
 } // extern "C"

@@ -39,6 +39,8 @@ struct RenderParams
     DevStats *stats;
     unsigned int *work_counter;
     u64 *rsl_scratch;              /* K1b: randrsl columns, 16*FFR_TPB words per block */
+    u64 *trace;                    /* FFR_SCATTER_TRACE: cell index of sample `it` of chain k at
+                                      trace[it*chain_count + k], ~0 when not plotted */
     u64 chain_first, chain_count, chain_len, last_len, base_seed, bv_limit;
     uint32_t blob_bytes, scatter_mode;
 };
@@ -55,6 +57,20 @@ __device__ __forceinline__ void stage_blob(DevFlame *dst, const DevFlame *src, u
     for (uint32_t i = threadIdx.x; i < bytes/8; i += blockDim.x)
         d[i] = s[i];
     __syncthreads();
+}
+
+/* add the 16-bit per-xform selection counters packed in pk0/pk1 to the block's counters */
+__device__ __forceinline__ void flush_packed(unsigned long long *s_xf, u64 &pk0, u64 &pk1)
+{
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+    {
+        const unsigned a0 = (unsigned)((pk0 >> (16*f)) & 0xffffu);
+        const unsigned a1 = (unsigned)((pk1 >> (16*f)) & 0xffffu);
+        if (a0) atomicAdd(&s_xf[f],(unsigned long long)a0);
+        if (a1) atomicAdd(&s_xf[4+f],(unsigned long long)a1);
+    }
+    pk0 = pk1 = 0;
 }
 
 /* colour loops: registers (fully unrolled, predicated) for RCAP <= 4, local memory beyond */
@@ -115,6 +131,8 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
     const double *__restrict__ colors = prm.colors;
     u64 *__restrict__ buffer = prm.buffer;
     const bool warp_agg = prm.scatter_mode == FFR_SCATTER_WARP_AGG;
+    const bool discard = prm.scatter_mode == FFR_SCATTER_DISCARD || prm.scatter_mode == FFR_SCATTER_TRACE;
+    u64 *__restrict__ trace = prm.scatter_mode == FFR_SCATTER_TRACE ? prm.trace : nullptr;
 
     Rng rng;
     rng.bind(rng_base,tid);
@@ -128,6 +146,7 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
        flushed to shared counters every 32768 iterations (one ballot per xform otherwise) */
     __shared__ unsigned long long s_xf[8];
     const bool packed_xf = nx <= 8;
+    const bool long_chain = prm.chain_len > 32768;  /* 16-bit fields: flush mid-chain too */
     u64 pk0 = 0, pk1 = 0;
     if (tid < 8)
         s_xf[tid] = 0;
@@ -141,7 +160,7 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
     }
 
     const u64 num_groups = (prm.chain_count + FFR_TPB - 1) / FFR_TPB;
-    const long long chain_len = (long long)prm.chain_len;
+    const int chain_len = (int)prm.chain_len;   /* host guarantees chain_len < 2^31 */
 
     for (;;)
     {
@@ -157,8 +176,8 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
             break;
         const u64 kk = g*FFR_TPB + tid;
         const bool active = kk < prm.chain_count;
-        const long long len = !active ? 0 :
-            ((kk+1 == prm.chain_count && prm.last_len) ? (long long)prm.last_len : chain_len);
+        const int len = !active ? 0 :
+            ((kk+1 == prm.chain_count && prm.last_len) ? (int)prm.last_len : chain_len);
         /* rng::setSeed((u64)seed_k) */
         rng.seed(splitmix64(prm.base_seed + prm.chain_first + kk));
 
@@ -172,7 +191,7 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
 
         /* iterations -53..-1 are the settle iterations of _init (no stats, no plotting);
            sharing the loop keeps one inlined copy of the xform interpreter */
-        for (long long it = -FFR_SETTLE_ITERS; it < chain_len; ++it)
+        for (int it = -FFR_SETTLE_ITERS; it < chain_len; ++it)
         {
             if (it == 0 && RCAP > 0)
             {
@@ -279,6 +298,8 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
 #pragma unroll
                             for (int i = 1; i < D; ++i)
                                 bi += __double2ull_rz((pf[i] - fl->lo[i]) * fl->mult_d[i]) * fl->mult_i[i];
+                            if (trace)
+                                trace[(u64)it*prm.chain_count + kk] = bi;
                             u64 *cell = buffer + bi*cellsz;
                             if (warp_agg)
                             {
@@ -287,9 +308,9 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
                                 if ((int)(__ffs(peers) - 1) == lane)
                                     atomicAdd(cell,(u64)__popc(peers));
                             }
-                            else
+                            else if (!discard)
                                 atomicAdd(cell,1ULL); /* :211-215 */
-                            if (RCAP > 0)
+                            if (RCAP > 0 && !discard)
                             {
                                 FOR_COLOR(i) /* :217-229 */
                                     atomicAdd((double*)(cell + 1 + i),cf[i]);
@@ -303,19 +324,10 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
                 /* xi == 0xffffffff (not alive) matches neither range */
                 const u64 inc = 1ULL << ((xi & 3u)*16u);
                 pk0 += (xi < 4u) ? inc : 0ULL;
-                pk1 += (xi - 4u < 4u) ? inc : 0ULL;
-                if ((it & 0x7fff) == 0x7fff || it == chain_len - 1)
-                {
-#pragma unroll
-                    for (int f = 0; f < 4; ++f)
-                    {
-                        const unsigned a0 = (unsigned)((pk0 >> (16*f)) & 0xffffu);
-                        const unsigned a1 = (unsigned)((pk1 >> (16*f)) & 0xffffu);
-                        if (a0) atomicAdd(&s_xf[f],(unsigned long long)a0);
-                        if (a1) atomicAdd(&s_xf[4+f],(unsigned long long)a1);
-                    }
-                    pk0 = pk1 = 0;
-                }
+                if (nx > 4)
+                    pk1 += (xi - 4u < 4u) ? inc : 0ULL;
+                if (long_chain && (it & 0x7fff) == 0x7fff)
+                    flush_packed(s_xf,pk0,pk1);
             }
             else if (it >= 0)
             {
@@ -332,6 +344,8 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
                 }
             }
         }
+        if (packed_xf)
+            flush_packed(s_xf,pk0,pk1);   /* fields hold at most one chain's selections */
     }
 
     /* merge statistics, buffer_renderer.hpp:232-246 */
@@ -416,6 +430,8 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
     const double *__restrict__ colors = prm.colors;
     u64 *__restrict__ buffer = prm.buffer;
     const bool warp_agg = prm.scatter_mode == FFR_SCATTER_WARP_AGG;
+    const bool discard = prm.scatter_mode == FFR_SCATTER_DISCARD || prm.scatter_mode == FFR_SCATTER_TRACE;
+    u64 *__restrict__ trace = prm.scatter_mode == FFR_SCATTER_TRACE ? prm.trace : nullptr;
 
     u64 n_iter = 0, n_plot = 0;
     u64 xfc = 0;             /* warp 0, lane k: selections of xform k */
@@ -428,7 +444,7 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
     }
 
     const u64 num_groups = (prm.chain_count + FFR_TPB - 1) / FFR_TPB;
-    const long long chain_len = (long long)prm.chain_len;
+    const int chain_len = (int)prm.chain_len;   /* host guarantees chain_len < 2^31 */
 
 #define LOAD_RNG(R,slot) do { (R).col = rng_base + (slot); (R).rcol = rsl_base + (slot); (R).a = st_a[slot]; (R).b = st_b[slot]; \
         (R).c = st_c[slot]; (R).cnt = (int)st_n[slot]; } while (0)
@@ -447,8 +463,8 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
             break;
         const u64 kk = g*FFR_TPB + tid;
         const bool active = kk < prm.chain_count;
-        const long long len = !active ? 0 :
-            ((kk+1 == prm.chain_count && prm.last_len) ? (long long)prm.last_len : chain_len);
+        const int len = !active ? 0 :
+            ((kk+1 == prm.chain_count && prm.last_len) ? (int)prm.last_len : chain_len);
         bool dead = false;   /* owner-side flag of slot tid */
         {
             Rng rng;
@@ -462,7 +478,7 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
         }
         s_xi[tid] = 0;
 
-        for (long long it = -FFR_SETTLE_ITERS; it < chain_len; ++it)
+        for (int it = -FFR_SETTLE_ITERS; it < chain_len; ++it)
         {
             /* ---- A: owner draws ---- */
             Rng rng;
@@ -639,6 +655,8 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
 #pragma unroll
                             for (int i = 1; i < D; ++i)
                                 bi += __double2ull_rz((pf[i] - fl->lo[i]) * fl->mult_d[i]) * fl->mult_i[i];
+                            if (trace)
+                                trace[(u64)it*prm.chain_count + (g*FFR_TPB + s)] = bi;
                             u64 *cell = buffer + bi*cellsz;
                             if (warp_agg)
                             {
@@ -646,9 +664,9 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
                                 if ((int)(__ffs(pe) - 1) == lane)
                                     atomicAdd(cell,(u64)__popc(pe));
                             }
-                            else
+                            else if (!discard)
                                 atomicAdd(cell,1ULL);
-                            if (RCAP > 0)
+                            if (RCAP > 0 && !discard)
                             {
                                 FOR_COLOR(i)
                                     atomicAdd((double*)(cell + 1 + i),cf[i]);
@@ -856,6 +874,27 @@ __global__ void __launch_bounds__(FFR_TPB) isaac_words_kernel(u64 seed, u64 n, u
     if (threadIdx.x == 0)
         for (u64 i = 0; i < n; ++i)
             out[i] = rng.next();
+}
+
+/* M1b: attractor replay: the same RED mix at the cell indices a render of this flame produced
+   (FFR_SCATTER_TRACE), thread k replaying chain k in order, so warps collide on hot cells
+   exactly as the render's warps do -- the measured scatter roofline for THIS access pattern. */
+__global__ void __launch_bounds__(FFR_TPB) atomic_replay_kernel(u64 *buffer, const u64 *__restrict__ trace,
+        u64 chain_count, u64 chain_len, uint32_t cellsz)
+{
+    const u64 k = (u64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= chain_count)
+        return;
+    for (u64 it = 0; it < chain_len; ++it)
+    {
+        const u64 bi = trace[it*chain_count + k];
+        if (bi == ~0ULL)
+            continue;
+        u64 *cell = buffer + bi*cellsz;
+        atomicAdd(cell,1ULL);
+        for (uint32_t i = 1; i < cellsz; ++i)
+            atomicAdd((double*)(cell + i),0.5);
+    }
 }
 
 /* M1: random-atomic microbenchmark: same RED mix as the render kernel's scatter (1 u64 +

@@ -231,7 +231,10 @@ enum ffr_scatter_mode
     FFR_SCATTER_AUTO = 0,
     FFR_SCATTER_GLOBAL = 1,     /* one RED per element straight to L2/HBM */
     FFR_SCATTER_WARP_AGG = 2,   /* __match_any_sync aggregation of colliding lanes first */
-    FFR_SCATTER_SMEM_TILE = 3   /* shared-memory privatised hot tile + global fallback */
+    FFR_SCATTER_SMEM_TILE = 3,  /* shared-memory privatised hot tile + global fallback */
+    FFR_SCATTER_TRACE = 5,      /* internal to ffr_cuda_atomic_roofline pattern 1 */
+    FFR_SCATTER_DISCARD = 4     /* diagnostic: iterate and count but issue no REDs (measures the
+                                   compute-only rate for the roofline analysis; buffer untouched) */
 };
 
 typedef struct ffr_options
@@ -360,9 +363,14 @@ int ffr_cuda_isaac_words(ffr_ctx *ctx, uint64_t seed, uint64_t n, uint64_t *out)
 
 /* Random-atomic microbenchmark: the measured scatter roofline. Issues
    n_atomics REDs (1 u64 + color_dims f64 per cell) at pseudo-random cells of the
-   context's buffer with the render kernel's grid shape; returns elapsed ms (CUDA
-   events). pattern 0 = uniform cells, 1 = replay of the flame's own attractor. */
+   context's buffer with the render kernel's grid shape; returns elapsed ms (CUDA events).
+   pattern 0 = uniform cells; pattern 1 = replay of the flame's own attractor: a render of
+   resident_chains chains x (n_atomics / resident_chains) samples records every plotted cell
+   index, then the recorded stream is replayed as bare REDs (buffer contents are garbage
+   afterwards; statistics are restored). *n_done receives the number of cells actually hit. */
 int ffr_cuda_atomic_roofline(ffr_ctx *ctx, uint64_t n_atomics, int pattern, float *ms);
+int ffr_cuda_atomic_roofline_ex(ffr_ctx *ctx, uint64_t n_atomics, int pattern, float *ms,
+        uint64_t *n_done);
 
 #ifdef __cplusplus
 }

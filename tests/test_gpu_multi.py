@@ -102,3 +102,20 @@ def test_ffr_buf_cli_roundtrip(ffr, po, examples, tmp_path):
     assert p.returncode == 0, p.stderr
     assert "(not rendering)" in p.stderr
     assert np.array_equal(np.fromfile(out2, dtype=np.uint64), 2 * a)
+
+
+def test_atomic_roofline_patterns(ffr, examples):
+    """The scatter microbenchmarks: uniform cells and attractor replay both run,
+    report how many cells they hit, and leave the render statistics untouched."""
+    fl = ffr.Flame(examples.example_json("barnsley_fern", size=[256, 256]))
+    r = ffr.BufferRenderer(fl)
+    r.render_chains(0, 512, 256, base_seed=1)
+    before = r.fetch_stats()
+    ms0, n0 = r.atomic_roofline(1 << 22, pattern=0)
+    ms1, n1 = r.atomic_roofline(1 << 22, pattern=1)
+    assert ms0 > 0 and ms1 > 0
+    assert n0 >= (1 << 22) * 0.5
+    # the fern plots every sample, so the replay hits one cell per recorded sample
+    assert n1 == (max(1, (1 << 22) // r.resident_chains)) * r.resident_chains
+    assert r.fetch_stats() == before
+    r.close()
