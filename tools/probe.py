@@ -3,6 +3,8 @@ render_chains for the BASELINE configs. Usage: python tools/probe.py [name ...]"
 import importlib, sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 ffr = importlib.import_module("flame-fractal-renderer_b200")
+if os.environ.get("FFR_LIB"):  # development only: probe an experimental build of the library
+    ffr.LIB_PATH = os.environ["FFR_LIB"]
 ex = importlib.import_module("flame-fractal-renderer_b200.examples")
 
 CONFIGS = {
