@@ -229,7 +229,10 @@ int iterate_points(const Json& j, int64_t xf_index, u64 n, const u64 *seeds,
     for (u64 i = 0; i < n; ++i)
     {
         rng::setSeed((u64)seeds[i]);
-        Point<num_t,dims> p(pts_in + dims*i);
+        num_t tmp[dims];
+        for (size_t d = 0; d < dims; ++d)
+            tmp[d] = (num_t)pts_in[dims*i+d]; // the float build takes float points
+        Point<num_t,dims> p(tmp);
         Point<num_t,dims> q = xf->applyIteration(p);
         for (size_t d = 0; d < dims; ++d)
             pts_out[dims*i+d] = q[d];
@@ -252,6 +255,10 @@ extern "C"
 const char *ref_last_error() { return g_err.c_str(); }
 
 u64 ref_splitmix64(u64 x) { return splitmix64(x); }
+
+// sizeof(num_t) == sizeof(hist_t): 8 for the shipped double/u64 build, 4 for the float/u32
+// configuration (types.hpp:24-41)
+int ref_elem_size() { return (int)sizeof(hist_t); }
 
 void ref_isaac_words(u64 seed, u64 n, u64 *out)
 {
