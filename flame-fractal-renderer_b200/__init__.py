@@ -111,6 +111,8 @@ ABI = {
     "ffr_flame_from_json": (C.c_void_p, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "ffr_flame_from_json_sized": (C.c_void_p, [C.c_char_p, C.c_size_t, _u64p, C.c_int,
                                                C.c_char_p, C.c_size_t]),
+    "ffr_flame_from_json_ex": (C.c_void_p, [C.c_char_p, C.c_size_t, _u64p, C.c_int, C.c_int,
+                                            C.c_char_p, C.c_size_t]),
     "ffr_flame_get_desc": (_descp, [C.c_void_p]),
     "ffr_flame_free": (None, [C.c_void_p]),
     "ffr_flame_layout": (C.c_int, [_descp, _f64p, _u64p, _u64p, _u64p]),
@@ -181,15 +183,14 @@ class FfrError(RuntimeError):
 class Flame:
     """Flame<dims>(json): parse + validate + flatten a flame JSON text (FLAME_JSON.md)."""
 
-    def __init__(self, text, size=None):
+    def __init__(self, text, size=None, elem_size=8):
+        """elem_size 8: the shipped double/uint64_t build; 4: the float/uint32_t build."""
         if isinstance(text, str):
             text = text.encode()
         err = C.create_string_buffer(512)
-        if size is None:
-            h = lib().ffr_flame_from_json(text, len(text), err, len(err))
-        else:
-            arr = (C.c_uint64 * len(size))(*size)
-            h = lib().ffr_flame_from_json_sized(text, len(text), arr, len(size), err, len(err))
+        arr = (C.c_uint64 * len(size))(*size) if size is not None else None
+        h = lib().ffr_flame_from_json_ex(text, len(text), arr, len(size) if size is not None else 0,
+                                         elem_size, err, len(err))
         if not h:
             raise FfrError(err.value.decode())
         self._h = h
@@ -197,9 +198,13 @@ class Flame:
         self.desc = self.desc_p.contents
 
     @classmethod
-    def from_file(cls, path, size=None):
+    def from_file(cls, path, size=None, elem_size=8):
         with open(path, "rb") as f:
-            return cls(f.read(), size=size)
+            return cls(f.read(), size=size, elem_size=elem_size)
+
+    @property
+    def elem_size(self):
+        return self.desc.elem_size
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -278,6 +283,8 @@ class BufferRenderer:
             raise FfrError(err.value.decode())
         self.bytes = L.ffr_cuda_buffer_bytes(self._h)
         self.cells = L.ffr_cuda_buffer_cells(self._h)
+        self.elem_size = flame.elem_size
+        self.word_dtype = np.uint64 if self.elem_size == 8 else np.uint32
         self.cell_size = 1 + flame.color_dims
         self._stats = FfrStats()
 
@@ -346,9 +353,10 @@ class BufferRenderer:
         return lib().ffr_cuda_device_buffer(self._h, dev_index)
 
     def read_buffer(self, out=None):
-        """writeBuffer(): the raw buffer, cells x (1 + color_dims) 8-byte elements as uint64."""
+        """writeBuffer(): the raw buffer, cells x (1 + color_dims) elements, as uint64 (double
+        build) or uint32 (float build) words."""
         if out is None:
-            out = np.empty(self.bytes // 8, dtype=np.uint64)
+            out = np.empty(self.bytes // self.elem_size, dtype=self.word_dtype)
         self._check(lib().ffr_cuda_read_buffer(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
@@ -394,8 +402,11 @@ class BufferRenderer:
 
 
 def split_counts_colors(raw, cells, color_dims):
-    """Split a raw reference-layout buffer (uint64 view) into (counts u64, colours f64)."""
-    a = np.asarray(raw).view(np.uint64).reshape(cells, 1 + color_dims)
+    """Split a raw reference-layout buffer into (counts, colour sums): u64/f64 for the double
+    build, u32/f32 for the float build (decided by the array's word size)."""
+    raw = np.asarray(raw)
+    wd, fd = (np.uint64, np.float64) if raw.dtype.itemsize == 8 else (np.uint32, np.float32)
+    a = raw.view(wd).reshape(cells, 1 + color_dims)
     counts = a[:, 0].copy()
-    colors = a[:, 1:].copy().view(np.float64) if color_dims else None
+    colors = a[:, 1:].copy().view(fd) if color_dims else None
     return counts, colors

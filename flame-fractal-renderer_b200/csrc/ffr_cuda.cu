@@ -14,7 +14,7 @@ point that computes needs an sm_100 device and fails loudly without one.
 
 #include "ffr_kernels.cuh"
 
-#define FFR_VERSION_STRING "ffr-b200 0.1 (sm_100a, double/u64)"
+#define FFR_VERSION_STRING "ffr-b200 0.2 (sm_100a, double/u64 + float/u32)"
 
 namespace
 {
@@ -94,21 +94,45 @@ void isaac_m0(u64 m[16])
 #undef MIX
 }
 
+/* same for Isaac<u32,4>: mix (u32) isaac.hpp:158-169, golden ratio 0x9e3779b9 */
+void isaac_m0_32(unsigned int m[16])
+{
+    unsigned int a,b,c,d,e,f,g,h;
+    a = b = c = d = e = f = g = h = 0x9e3779b9u;
+#define MIX32() do { \
+    a ^= b << 11; d += a; b += c; \
+    b ^= c >>  2; e += b; c += d; \
+    c ^= d <<  8; f += c; d += e; \
+    d ^= e >> 16; g += d; e += f; \
+    e ^= f << 10; h += e; f += g; \
+    f ^= g >>  4; a += f; g += h; \
+    g ^= h <<  8; b += g; h += a; \
+    h ^= a >>  9; c += h; a += b; } while (0)
+    MIX32(); MIX32(); MIX32(); MIX32();
+    for (int i = 0; i < 16; i += 8)
+    {
+        MIX32();
+        m[i+0] = a; m[i+1] = b; m[i+2] = c; m[i+3] = d;
+        m[i+4] = e; m[i+5] = f; m[i+6] = g; m[i+7] = h;
+    }
+#undef MIX32
+}
+
 struct DeviceState
 {
     int dev = -1;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    u64 *buffer = nullptr;
+    void *buffer = nullptr;        /* cells x (1+r) elements of ctx->elem bytes */
     bool own_buffer = false;
-    DevFlame *d_blob = nullptr;
-    double *d_colors = nullptr;
+    void *d_blob = nullptr;
+    void *d_colors = nullptr;
     DevStats *d_stats = nullptr;
     unsigned int *d_counter = nullptr;
     u64 *d_scratch = nullptr;      /* 2 x u64 for histogram sum/max */
-    u64 *d_rsl = nullptr;          /* K1b randrsl scratch */
+    void *d_rsl = nullptr;         /* K1b randrsl scratch */
     u64 *d_trace = nullptr;        /* only while ffr_cuda_atomic_roofline records a trace */
-    u64 *d_stage = nullptr;        /* staging for add_buffer, kept between calls */
+    void *d_stage = nullptr;       /* staging for add_buffer, kept between calls */
     size_t stage_elems = 0;
     int sm_count = 0;
     int blocks_per_sm = 0;
@@ -122,6 +146,7 @@ typedef void (*render_fn)(const RenderParams);
 struct ffr_ctx
 {
     uint32_t dims = 0, r = 0, cellsz = 1;
+    uint32_t elem = 8;             /* sizeof(num_t) == sizeof(hist_t): 8 double/u64, 4 float/u32 */
     uint32_t size0 = 1, size1 = 1;
     u64 cells = 0;
     size_t bytes = 0;
@@ -130,7 +155,7 @@ struct ffr_ctx
     uint32_t distinct_oplists = 1;
     double divergence_ratio = 1.0;
     std::vector<unsigned char> blob;
-    std::vector<double> colors;
+    std::vector<unsigned char> colors;   /* T[]: xform colours in the build's precision */
     std::vector<u64> json_ids;     /* sorted index -> JSON id */
     std::vector<DeviceState> devs;
     ffr_options opt;
@@ -161,49 +186,52 @@ bool cuda_ok(ffr_ctx *ctx, cudaError_t e, const char *what)
 
 #define CK(call) do { if (!cuda_ok(ctx,(call),#call)) return FFR_E_CUDA; } while (0)
 
-template <int D, int RCAP>
+template <typename T, int D, int RCAP>
 render_fn pick_affine(bool affine_only)
 {
-    return affine_only ? (render_fn)render_kernel<D,RCAP,true> : (render_fn)render_kernel<D,RCAP,false>;
+    return affine_only ? (render_fn)render_kernel<T,D,RCAP,true> : (render_fn)render_kernel<T,D,RCAP,false>;
 }
 
-template <int D>
+template <typename T, int D>
 render_fn pick_rcap(uint32_t r, bool affine_only)
 {
-    if (r == 0) return pick_affine<D,0>(affine_only);
-    if (r <= 4) return pick_affine<D,4>(affine_only);
-    return pick_affine<D,FFR_MAX_COLOR_DIMS>(affine_only);
+    if (r == 0) return pick_affine<T,D,0>(affine_only);
+    if (r <= 4) return pick_affine<T,D,4>(affine_only);
+    return pick_affine<T,D,FFR_MAX_COLOR_DIMS>(affine_only);
 }
 
 /* regroup variant: colour dims <= 4 only */
+template <typename T>
 render_fn pick_regroup(uint32_t dims, uint32_t r, size_t *extra_smem)
 {
     const int rc = (r == 0) ? 0 : 4;
-    *extra_smem = FFR_SMEM_REGROUP_BYTES(dims,rc);
+    *extra_smem = FFR_SMEM_REGROUP_BYTES(dims,rc,sizeof(T));
     switch (dims*10 + rc)
     {
-    case 10: return (render_fn)render_kernel_regroup<1,0>;
-    case 14: return (render_fn)render_kernel_regroup<1,4>;
-    case 20: return (render_fn)render_kernel_regroup<2,0>;
-    case 24: return (render_fn)render_kernel_regroup<2,4>;
-    case 30: return (render_fn)render_kernel_regroup<3,0>;
-    case 34: return (render_fn)render_kernel_regroup<3,4>;
+    case 10: return (render_fn)render_kernel_regroup<T,1,0>;
+    case 14: return (render_fn)render_kernel_regroup<T,1,4>;
+    case 20: return (render_fn)render_kernel_regroup<T,2,0>;
+    case 24: return (render_fn)render_kernel_regroup<T,2,4>;
+    case 30: return (render_fn)render_kernel_regroup<T,3,0>;
+    case 34: return (render_fn)render_kernel_regroup<T,3,4>;
     default: return nullptr;
     }
 }
 
+template <typename T>
 render_fn pick_kernel(uint32_t dims, uint32_t r, bool affine_only)
 {
     switch (dims)
     {
-    case 1: return pick_rcap<1>(r,affine_only);
-    case 2: return pick_rcap<2>(r,affine_only);
-    case 3: return pick_rcap<3>(r,affine_only);
+    case 1: return pick_rcap<T,1>(r,affine_only);
+    case 2: return pick_rcap<T,2>(r,affine_only);
+    case 3: return pick_rcap<T,3>(r,affine_only);
     default: return nullptr;
     }
 }
 
 /* flatten the caller's desc into the device blob (DevFlame | DevXForm[] | DevVar[]) */
+template <typename T>
 bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
 {
     if (!d || d->dims < 1 || d->dims > FFR_MAX_DIMS)
@@ -211,9 +239,9 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
         err = "dimensions not supported";
         return false;
     }
-    if (d->elem_size != 8)
+    if (d->elem_size != sizeof(T))
     {
-        err = "only the double/u64 build (elem_size 8) is implemented";
+        err = "elem_size must be 8 (double/u64) or 4 (float/u32)";
         return false;
     }
     if (d->color_dims > FFR_MAX_COLOR_DIMS)
@@ -231,15 +259,17 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
         err = "libffr_cuda supports at most 64 xforms";
         return false;
     }
-    DevFlame hdr;
+    DevFlameT<T> hdr;
     memset(&hdr,0,sizeof(hdr));
     hdr.dims = d->dims;
     hdr.r = d->color_dims;
     hdr.has_final = d->has_final && d->final_xform;
     hdr.num_xforms = d->num_xforms;
     hdr.num_ids = d->num_xform_ids;
-    /* BufferRenderer::_init, buffer_renderer.hpp:114-140 */
-    const double scale_adjust_down = 1.0 - (double)(float)(1.0 / (double)(1L << 52));
+    /* BufferRenderer::_init, buffer_renderer.hpp:114-140, in num_t arithmetic;
+       scale_adjust_down_v<num_t> = 1 - emach (constants.hpp:25-30,59-62) */
+    const T scale_adjust_down = sizeof(T) == 8 ? (T)(1.0 - (double)(float)(1.0 / (double)(1L << 52)))
+                                               : (T)(1.0F - 1.0F / (float)(1 << 23));
     u64 cells = 1;
     for (uint32_t i = 0; i < d->dims; ++i)
     {
@@ -248,9 +278,9 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
             err = "Flame(): bad size or bounds";
             return false;
         }
-        hdr.lo[i] = d->bounds_lo[i];
-        hdr.hi[i] = d->bounds_hi[i];
-        hdr.mult_d[i] = (double)(d->size[i]) / (d->bounds_hi[i] - d->bounds_lo[i]);
+        hdr.lo[i] = (T)d->bounds_lo[i];
+        hdr.hi[i] = (T)d->bounds_hi[i];
+        hdr.mult_d[i] = (T)(d->size[i]) / (hdr.hi[i] - hdr.lo[i]);
         hdr.mult_d[i] *= scale_adjust_down;
         hdr.mult_i[i] = cells;
         cells *= d->size[i];
@@ -263,24 +293,30 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
     hdr.cells = cells;
     hdr.cell = 1 + d->color_dims;
     for (uint32_t i = 0; i < FFR_MAX_XFORMS; ++i)
-        hdr.xfcw[i] = (i < d->num_xforms) ? d->xfcw[i] : 2.0; /* padding never < r, see select_xform */
+        hdr.xfcw[i] = (i < d->num_xforms) ? (T)d->xfcw[i] : (T)2.0; /* padding never < r */
 
-    std::vector<DevXForm> xfs;
-    std::vector<DevVar> vars;
-    ctx->colors.clear();
+    std::vector<DevXFormT<T>> xfs;
+    std::vector<DevVarT<T>> vars;
+    std::vector<T> colors;
     ctx->json_ids.clear();
     bool affine_only = true, uses_rng = false;
     const uint32_t total = d->num_xforms + (hdr.has_final ? 1 : 0);
     for (uint32_t i = 0; i < total; ++i)
     {
         const ffr_xform &x = (i < d->num_xforms) ? d->xforms[i] : *d->final_xform;
-        DevXForm dx;
+        DevXFormT<T> dx;
         memset(&dx,0,sizeof(dx));
-        memcpy(dx.pre_A,x.pre_A,sizeof(dx.pre_A));
-        memcpy(dx.pre_b,x.pre_b,sizeof(dx.pre_b));
-        memcpy(dx.post_A,x.post_A,sizeof(dx.post_A));
-        memcpy(dx.post_b,x.post_b,sizeof(dx.post_b));
-        dx.color_speed = x.color_speed;
+        for (int k = 0; k < 9; ++k)
+        {
+            dx.pre_A[k] = (T)x.pre_A[k];
+            dx.post_A[k] = (T)x.post_A[k];
+        }
+        for (int k = 0; k < 3; ++k)
+        {
+            dx.pre_b[k] = (T)x.pre_b[k];
+            dx.post_b[k] = (T)x.post_b[k];
+        }
+        dx.color_speed = (T)x.color_speed;
         dx.var_begin = (uint32_t)vars.size();
         dx.var_count = x.num_vars;
         dx.flags = (x.has_pre ? XF_HAS_PRE : 0) | (x.has_post ? XF_HAS_POST : 0);
@@ -299,9 +335,9 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
         if (x.has_color && x.color && d->color_dims)
         {
             dx.flags |= XF_HAS_COLOR;
-            dx.color_off = (uint32_t)ctx->colors.size();
+            dx.color_off = (uint32_t)colors.size();
             for (uint32_t k = 0; k < d->color_dims; ++k)
-                ctx->colors.push_back(x.color[k]);
+                colors.push_back((T)x.color[k]);
         }
         for (uint32_t k = 0; k < x.num_vars; ++k)
         {
@@ -322,14 +358,15 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
                 err = "axis index out of range";
                 return false;
             }
-            DevVar dv;
+            DevVarT<T> dv;
             memset(&dv,0,sizeof(dv));
             dv.op = v.op;
             dv.axis_x = (d->dims == 2) ? 0 : v.axis_x;
             dv.axis_y = (d->dims == 2) ? 1 : v.axis_y;
             dv.need = op_need(v.op) | (var_uses_rng(v.op) ? NEED_RNG : 0u);
-            dv.weight = v.weight;
-            memcpy(dv.p,v.params,sizeof(dv.p));
+            dv.weight = (T)v.weight;
+            for (int q = 0; q < FFR_MAX_VAR_PARAMS; ++q)
+                dv.p[q] = (T)v.params[q];
             dx.need |= dv.need;
             if (v.op != FFR_VAR_LINEAR)
                 affine_only = false;
@@ -385,13 +422,15 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
         }
         ctx->divergence_ratio = direct / grouped;
     }
-    if (ctx->colors.empty())
-        ctx->colors.push_back(0.0);
+    if (colors.empty())
+        colors.push_back((T)0);
+    ctx->colors.assign((const unsigned char*)colors.data(),
+        (const unsigned char*)colors.data() + colors.size()*sizeof(T));
     hdr.num_vars = (uint32_t)vars.size();
     hdr.uses_rng = uses_rng;
-    hdr.xf_off = (uint32_t)sizeof(DevFlame);
-    hdr.var_off = hdr.xf_off + (uint32_t)(xfs.size()*sizeof(DevXForm));
-    hdr.total_bytes = hdr.var_off + (uint32_t)(vars.size()*sizeof(DevVar));
+    hdr.xf_off = (uint32_t)sizeof(DevFlameT<T>);
+    hdr.var_off = hdr.xf_off + (uint32_t)(xfs.size()*sizeof(DevXFormT<T>));
+    hdr.total_bytes = hdr.var_off + (uint32_t)(vars.size()*sizeof(DevVarT<T>));
     hdr.total_bytes = (hdr.total_bytes + 15u) & ~15u;
     if (hdr.total_bytes > 96*1024)
     {
@@ -400,16 +439,17 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
     }
     ctx->blob.assign(hdr.total_bytes,0);
     memcpy(ctx->blob.data(),&hdr,sizeof(hdr));
-    memcpy(ctx->blob.data()+hdr.xf_off,xfs.data(),xfs.size()*sizeof(DevXForm));
+    memcpy(ctx->blob.data()+hdr.xf_off,xfs.data(),xfs.size()*sizeof(DevXFormT<T>));
     if (!vars.empty())
-        memcpy(ctx->blob.data()+hdr.var_off,vars.data(),vars.size()*sizeof(DevVar));
+        memcpy(ctx->blob.data()+hdr.var_off,vars.data(),vars.size()*sizeof(DevVarT<T>));
     ctx->dims = d->dims;
     ctx->size0 = (uint32_t)d->size[0];
     ctx->size1 = d->dims > 1 ? (uint32_t)d->size[1] : 1;
     ctx->r = d->color_dims;
     ctx->cellsz = hdr.cell;
     ctx->cells = cells;
-    ctx->bytes = (size_t)cells*hdr.cell*8;
+    ctx->elem = (uint32_t)sizeof(T);
+    ctx->bytes = (size_t)cells*hdr.cell*sizeof(T);
     ctx->num_xforms = d->num_xforms;
     ctx->num_ids = d->num_xform_ids;
     ctx->has_final = hdr.has_final;
@@ -457,8 +497,8 @@ int setup_device(ffr_ctx *ctx, DeviceState &ds, int dev, const ffr_options &opt)
     }
     CK(cudaMalloc(&ds.d_blob,ctx->blob.size()));
     CK(cudaMemcpyAsync(ds.d_blob,ctx->blob.data(),ctx->blob.size(),cudaMemcpyHostToDevice,ds.stream));
-    CK(cudaMalloc(&ds.d_colors,ctx->colors.size()*sizeof(double)));
-    CK(cudaMemcpyAsync(ds.d_colors,ctx->colors.data(),ctx->colors.size()*sizeof(double),
+    CK(cudaMalloc(&ds.d_colors,ctx->colors.size()));
+    CK(cudaMemcpyAsync(ds.d_colors,ctx->colors.data(),ctx->colors.size(),
         cudaMemcpyHostToDevice,ds.stream));
     CK(cudaMalloc(&ds.d_stats,sizeof(DevStats)));
     DevStats init;
@@ -469,6 +509,9 @@ int setup_device(ffr_ctx *ctx, DeviceState &ds, int dev, const ffr_options &opt)
     u64 m0[16];
     isaac_m0(m0);
     CK(cudaMemcpyToSymbolAsync(c_isaac_m0,m0,sizeof(m0),0,cudaMemcpyHostToDevice,ds.stream));
+    unsigned int m0_32[16];
+    isaac_m0_32(m0_32);
+    CK(cudaMemcpyToSymbolAsync(c_isaac_m0_32,m0_32,sizeof(m0_32),0,cudaMemcpyHostToDevice,ds.stream));
     CK(cudaFuncSetAttribute((const void*)ctx->kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,
         (int)ctx->smem_bytes));
     int nb = 0;
@@ -482,7 +525,7 @@ int setup_device(ffr_ctx *ctx, DeviceState &ds, int dev, const ffr_options &opt)
         nb = (int)opt.blocks_per_sm;
     ds.blocks_per_sm = nb;
     if (ctx->regroup)
-        CK(cudaMalloc(&ds.d_rsl,(size_t)ds.sm_count*nb*16*FFR_TPB*sizeof(u64)));
+        CK(cudaMalloc(&ds.d_rsl,(size_t)ds.sm_count*nb*16*FFR_TPB*ctx->elem));
     CK(cudaStreamSynchronize(ds.stream));
     return FFR_OK;
 }
@@ -642,7 +685,8 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
     if (opt)
         memcpy(&ctx->opt,opt,std::min<size_t>(opt->struct_size ? opt->struct_size : sizeof(ffr_options),
             sizeof(ffr_options)));
-    if (!pack_blob(ctx,desc,msg))
+    const bool f32 = desc && desc->elem_size == 4;
+    if (!(f32 ? pack_blob<float>(ctx,desc,msg) : pack_blob<double>(ctx,desc,msg)))
         return fail(msg);
     if (ndev < 1)
         return fail("ffr_cuda_create(): need at least one device");
@@ -654,8 +698,9 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
     ctx->scatter_mode = ctx->opt.scatter_mode;
     if (ctx->scatter_mode == FFR_SCATTER_AUTO || ctx->scatter_mode == FFR_SCATTER_SMEM_TILE)
         ctx->scatter_mode = FFR_SCATTER_GLOBAL;
-    ctx->kernel = pick_kernel(ctx->dims,ctx->r,ctx->affine_only);
-    ctx->smem_bytes = FFR_SMEM_RNG_BYTES + ctx->blob.size();
+    ctx->kernel = f32 ? pick_kernel<float>(ctx->dims,ctx->r,ctx->affine_only)
+                      : pick_kernel<double>(ctx->dims,ctx->r,ctx->affine_only);
+    ctx->smem_bytes = FFR_SMEM_RNG_BYTES_W(ctx->elem) + ctx->blob.size();
     /* regroup (K1b) when lanes would otherwise diverge over different op lists */
     ctx->regroup = false;
     if (ctx->opt.regroup != 1 && ctx->r <= 4 && ctx->num_xforms <= 31 &&
@@ -663,7 +708,8 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
          (ctx->distinct_oplists >= 2 && ctx->divergence_ratio > 2.2)))
     {
         size_t extra = 0;
-        render_fn k = pick_regroup(ctx->dims,ctx->r,&extra);
+        render_fn k = f32 ? pick_regroup<float>(ctx->dims,ctx->r,&extra)
+                          : pick_regroup<double>(ctx->dims,ctx->r,&extra);
         if (k)
         {
             ctx->kernel = k;
@@ -743,8 +789,9 @@ int ffr_cuda_add_buffer(ffr_ctx *ctx, const void *host, size_t bytes)
     CK(cudaSetDevice(ds.dev));
     /* stage in chunks so a 1 GiB -i file does not double the footprint; the staging buffer
        is kept for the next call */
-    const size_t chunk_elems = (size_t)1 << 24; /* 128 MiB */
-    const size_t n_elems = bytes/8;
+    const size_t eb = ctx->elem;
+    const size_t chunk_elems = ((size_t)1 << 27) / eb; /* 128 MiB */
+    const size_t n_elems = bytes/eb;
     size_t chunk = std::min(n_elems,chunk_elems - (chunk_elems % ctx->cellsz));
     if (ds.stage_elems < chunk)
     {
@@ -752,16 +799,20 @@ int ffr_cuda_add_buffer(ffr_ctx *ctx, const void *host, size_t bytes)
             cudaFree(ds.d_stage);
         ds.d_stage = nullptr;
         ds.stage_elems = 0;
-        CK(cudaMalloc(&ds.d_stage,chunk*8));
+        CK(cudaMalloc(&ds.d_stage,chunk*eb));
         ds.stage_elems = chunk;
     }
-    u64 *tmp = ds.d_stage;
+    void *tmp = ds.d_stage;
     for (size_t off = 0; off < n_elems; off += chunk)
     {
         size_t n = std::min(chunk,n_elems - off);
-        CK(cudaMemcpyAsync(tmp,(const u64*)host + off,n*8,cudaMemcpyHostToDevice,ds.stream));
+        CK(cudaMemcpyAsync(tmp,(const char*)host + off*eb,n*eb,cudaMemcpyHostToDevice,ds.stream));
         unsigned grid = (unsigned)std::min<size_t>((n + 255)/256,(size_t)ds.sm_count*16);
-        add_buffer_kernel<<<grid,256,0,ds.stream>>>(ds.buffer + off,tmp,n,ctx->cellsz);
+        if (eb == 8)
+            add_buffer_kernel<double><<<grid,256,0,ds.stream>>>((u64*)ds.buffer + off,(const u64*)tmp,n,ctx->cellsz);
+        else
+            add_buffer_kernel<float><<<grid,256,0,ds.stream>>>((unsigned int*)ds.buffer + off,
+                (const unsigned int*)tmp,n,ctx->cellsz);
         ++ctx->launches;
         CK(cudaGetLastError());
         /* the staging buffer is reused by the next chunk and the host buffer is only borrowed */
@@ -939,7 +990,7 @@ int ffr_cuda_reduce(ffr_ctx *ctx)
     int rc = sync_all(ctx);
     if (rc != FFR_OK)
         return rc;
-    const size_t n_elems = ctx->bytes/8;
+    const size_t n_elems = ctx->bytes/ctx->elem;
     for (size_t i = 1; i < ctx->devs.size(); ++i)
     {
         DeviceState &ds = ctx->devs[i];
@@ -948,8 +999,8 @@ int ffr_cuda_reduce(ffr_ctx *ctx)
         CK(cudaSetDevice(d0.dev));
         int can = 0;
         CK(cudaDeviceCanAccessPeer(&can,d0.dev,ds.dev));
-        const u64 *src = ds.buffer;
-        u64 *staged = nullptr;
+        const void *src = ds.buffer;
+        void *staged = nullptr;
         if (can)
         {
             cudaError_t e = cudaDeviceEnablePeerAccess(ds.dev,0);
@@ -967,7 +1018,11 @@ int ffr_cuda_reduce(ffr_ctx *ctx)
         }
         /* device 0 pulls the peer's buffer over NVLink and adds it, typed by position */
         unsigned grid = (unsigned)std::min<size_t>((n_elems + 255)/256,(size_t)d0.sm_count*16);
-        add_buffer_kernel<<<grid,256,0,d0.stream>>>(d0.buffer,src,n_elems,ctx->cellsz);
+        if (ctx->elem == 8)
+            add_buffer_kernel<double><<<grid,256,0,d0.stream>>>((u64*)d0.buffer,(const u64*)src,n_elems,ctx->cellsz);
+        else
+            add_buffer_kernel<float><<<grid,256,0,d0.stream>>>((unsigned int*)d0.buffer,
+                (const unsigned int*)src,n_elems,ctx->cellsz);
         ++ctx->launches;
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(d0.stream));
@@ -1012,8 +1067,12 @@ int ffr_cuda_histogram_sum_max(ffr_ctx *ctx, uint64_t *sum, uint64_t *max)
     CK(cudaSetDevice(ds.dev));
     CK(cudaMemsetAsync(ds.d_scratch,0,2*sizeof(u64),ds.stream));
     unsigned grid = (unsigned)std::min<u64>((ctx->cells + 255)/256,(u64)ds.sm_count*16);
-    hist_sum_max_kernel<<<grid,256,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,ds.d_scratch,
-        ds.d_scratch+1);
+    if (ctx->elem == 8)
+        hist_sum_max_kernel<u64><<<grid,256,0,ds.stream>>>((const u64*)ds.buffer,ctx->cells,ctx->cellsz,
+            ds.d_scratch,ds.d_scratch+1);
+    else
+        hist_sum_max_kernel<unsigned int><<<grid,256,0,ds.stream>>>((const unsigned int*)ds.buffer,
+            ctx->cells,ctx->cellsz,ds.d_scratch,ds.d_scratch+1);
     ++ctx->launches;
     CK(cudaGetLastError());
     u64 h[2];
@@ -1071,8 +1130,12 @@ int ffr_cuda_tonemap(ffr_ctx *ctx, int mode, int bits, double gamma, void *pixel
     const u64 init[2] = {~0ULL,0ULL};
     CK(cudaMemcpyAsync(ds.d_scratch,init,sizeof(init),cudaMemcpyHostToDevice,ds.stream));
     unsigned grid = (unsigned)std::min<u64>((ctx->cells + 255)/256,(u64)ds.sm_count*16);
-    hist_min_max_kernel<<<grid,256,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,ds.d_scratch,
-        ds.d_scratch+1);
+    if (ctx->elem == 8)
+        hist_min_max_kernel<u64><<<grid,256,0,ds.stream>>>((const u64*)ds.buffer,ctx->cells,ctx->cellsz,
+            ds.d_scratch,ds.d_scratch+1);
+    else
+        hist_min_max_kernel<unsigned int><<<grid,256,0,ds.stream>>>((const unsigned int*)ds.buffer,
+            ctx->cells,ctx->cellsz,ds.d_scratch,ds.d_scratch+1);
     ++ctx->launches;
     CK(cudaGetLastError());
     u64 mm[2];
@@ -1097,13 +1160,27 @@ int ffr_cuda_tonemap(ffr_ctx *ctx, int mode, int bits, double gamma, void *pixel
     }
     void *d_pix = nullptr;
     CK(cudaMalloc(&d_pix,need));
-    const double gp = 1.0 / gamma; /* :235 */
-    if (bits == 8)
-        tonemap_kernel<unsigned char><<<grid,256,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,mode,
-            mm[1],gp,(unsigned char*)d_pix);
+    /* num_t gp = 1.0 / arg_gamma (:235); arg_gamma is a num_t */
+    if (ctx->elem == 8)
+    {
+        const double gp = 1.0 / gamma;
+        if (bits == 8)
+            tonemap_kernel<double,unsigned char><<<grid,256,0,ds.stream>>>((const u64*)ds.buffer,ctx->cells,
+                ctx->cellsz,mode,mm[1],gp,(unsigned char*)d_pix);
+        else
+            tonemap_kernel<double,unsigned short><<<grid,256,0,ds.stream>>>((const u64*)ds.buffer,ctx->cells,
+                ctx->cellsz,mode,mm[1],gp,(unsigned short*)d_pix);
+    }
     else
-        tonemap_kernel<unsigned short><<<grid,256,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,mode,
-            mm[1],gp,(unsigned short*)d_pix);
+    {
+        const float gp = (float)(1.0 / (float)gamma);
+        if (bits == 8)
+            tonemap_kernel<float,unsigned char><<<grid,256,0,ds.stream>>>((const unsigned int*)ds.buffer,
+                ctx->cells,ctx->cellsz,mode,mm[1],gp,(unsigned char*)d_pix);
+        else
+            tonemap_kernel<float,unsigned short><<<grid,256,0,ds.stream>>>((const unsigned int*)ds.buffer,
+                ctx->cells,ctx->cellsz,mode,mm[1],gp,(unsigned short*)d_pix);
+    }
     ++ctx->launches;
     if (!cuda_ok(ctx,cudaGetLastError(),"tonemap_kernel") ||
         !cuda_ok(ctx,cudaMemcpyAsync(pixels,d_pix,need,cudaMemcpyDeviceToHost,ds.stream),"tonemap D2H") ||
@@ -1154,25 +1231,25 @@ int ffr_cuda_iterate_points(ffr_ctx *ctx, int64_t xf_index, uint64_t n, const ui
     CK(cudaMemcpyAsync(d_in,pts_in,pb,cudaMemcpyHostToDevice,ds.stream));
     const unsigned grid = (unsigned)((n + FFR_TPB - 1)/FFR_TPB);
     const uint32_t bb = (uint32_t)ctx->blob.size();
-    const size_t sm = FFR_SMEM_RNG_BYTES + ctx->blob.size();
-    switch (ctx->dims)
+    const size_t sm = FFR_SMEM_RNG_BYTES_W(ctx->elem) + ctx->blob.size();
+#define ITER_CASE(TT,DD) do { \
+        CK(cudaFuncSetAttribute((const void*)iterate_points_kernel<TT,DD>, \
+            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)sm)); \
+        iterate_points_kernel<TT,DD><<<grid,FFR_TPB,sm,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out); \
+    } while (0)
+    if (ctx->elem == 8)
     {
-    case 1:
-        CK(cudaFuncSetAttribute((const void*)iterate_points_kernel<1>,
-            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)sm));
-        iterate_points_kernel<1><<<grid,FFR_TPB,sm,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
-        break;
-    case 2:
-        CK(cudaFuncSetAttribute((const void*)iterate_points_kernel<2>,
-            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)sm));
-        iterate_points_kernel<2><<<grid,FFR_TPB,sm,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
-        break;
-    default:
-        CK(cudaFuncSetAttribute((const void*)iterate_points_kernel<3>,
-            cudaFuncAttributeMaxDynamicSharedMemorySize,(int)sm));
-        iterate_points_kernel<3><<<grid,FFR_TPB,sm,ds.stream>>>(ds.d_blob,bb,slot,n,d_seeds,d_in,d_out);
-        break;
+        if (ctx->dims == 1) ITER_CASE(double,1);
+        else if (ctx->dims == 2) ITER_CASE(double,2);
+        else ITER_CASE(double,3);
     }
+    else
+    {
+        if (ctx->dims == 1) ITER_CASE(float,1);
+        else if (ctx->dims == 2) ITER_CASE(float,2);
+        else ITER_CASE(float,3);
+    }
+#undef ITER_CASE
     ++ctx->launches;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(pts_out,d_out,pb,cudaMemcpyDeviceToHost,ds.stream));
@@ -1193,9 +1270,14 @@ int ffr_cuda_isaac_words(ffr_ctx *ctx, uint64_t seed, uint64_t n, uint64_t *out)
     CK(cudaSetDevice(ds.dev));
     u64 *d_out = nullptr;
     CK(cudaMalloc(&d_out,n*8));
-    CK(cudaFuncSetAttribute((const void*)isaac_words_kernel,
-        cudaFuncAttributeMaxDynamicSharedMemorySize,FFR_SMEM_RNG_BYTES));
-    isaac_words_kernel<<<1,FFR_TPB,FFR_SMEM_RNG_BYTES,ds.stream>>>(seed,n,d_out);
+    if (ctx->elem == 8)
+    {
+        CK(cudaFuncSetAttribute((const void*)isaac_words_kernel<double>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize,FFR_SMEM_RNG_BYTES_W(8)));
+        isaac_words_kernel<double><<<1,FFR_TPB,FFR_SMEM_RNG_BYTES_W(8),ds.stream>>>(seed,n,d_out);
+    }
+    else
+        isaac_words_kernel<float><<<1,FFR_TPB,FFR_SMEM_RNG_BYTES_W(4),ds.stream>>>(seed,n,d_out);
     ++ctx->launches;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out,d_out,n*8,cudaMemcpyDeviceToHost,ds.stream));
@@ -1231,8 +1313,12 @@ int ffr_cuda_atomic_roofline_ex(ffr_ctx *ctx, uint64_t n_atomics, int pattern, f
     if (pattern == 0)
     {
         CK(cudaEventRecord(e0,ds.stream));
-        atomic_bench_kernel<<<(unsigned)grid,FFR_TPB,0,ds.stream>>>(ds.buffer,ctx->cells,ctx->cellsz,
-            per_thread,0x1234u + ctx->launches);
+        if (ctx->elem == 8)
+            atomic_bench_kernel<double><<<(unsigned)grid,FFR_TPB,0,ds.stream>>>((u64*)ds.buffer,ctx->cells,
+                ctx->cellsz,per_thread,0x1234u + ctx->launches);
+        else
+            atomic_bench_kernel<float><<<(unsigned)grid,FFR_TPB,0,ds.stream>>>((unsigned int*)ds.buffer,
+                ctx->cells,ctx->cellsz,per_thread,0x1234u + ctx->launches);
         ++ctx->launches;
         CK(cudaGetLastError());
         CK(cudaEventRecord(e1,ds.stream));
@@ -1267,8 +1353,12 @@ int ffr_cuda_atomic_roofline_ex(ffr_ctx *ctx, uint64_t n_atomics, int pattern, f
                 *n_done = after.s_plot - before.s_plot;
             CK(cudaMemcpyAsync(ds.d_stats,saved,sizeof(DevStats),cudaMemcpyDeviceToDevice,ds.stream));
             CK(cudaEventRecord(e0,ds.stream));
-            atomic_replay_kernel<<<(unsigned)grid,FFR_TPB,0,ds.stream>>>(ds.buffer,trace,threads,per_thread,
-                ctx->cellsz);
+            if (ctx->elem == 8)
+                atomic_replay_kernel<double><<<(unsigned)grid,FFR_TPB,0,ds.stream>>>((u64*)ds.buffer,trace,
+                    threads,per_thread,ctx->cellsz);
+            else
+                atomic_replay_kernel<float><<<(unsigned)grid,FFR_TPB,0,ds.stream>>>((unsigned int*)ds.buffer,
+                    trace,threads,per_thread,ctx->cellsz);
             ++ctx->launches;
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1,ds.stream));

@@ -33,24 +33,25 @@ struct DevStats
 
 struct RenderParams
 {
-    const DevFlame *blob;
-    const double *colors;
-    u64 *buffer;
+    const void *blob;              /* DevFlameT<T> | DevXFormT<T>[] | DevVarT<T>[] */
+    const void *colors;            /* T[] */
+    void *buffer;                  /* cells x (1+r) elements of sizeof(T) bytes */
     DevStats *stats;
     unsigned int *work_counter;
-    u64 *rsl_scratch;              /* K1b: randrsl columns, 16*FFR_TPB words per block */
+    void *rsl_scratch;             /* K1b: randrsl columns, 16*FFR_TPB words per block */
     u64 *trace;                    /* FFR_SCATTER_TRACE: cell index of sample `it` of chain k at
                                       trace[it*chain_count + k], ~0 when not plotted */
     u64 chain_first, chain_count, chain_len, last_len, base_seed, bv_limit;
     uint32_t blob_bytes, scatter_mode;
 };
 
-#define FFR_SMEM_RNG_BYTES (FFR_RNG_WORDS*FFR_TPB*8)
+#define FFR_SMEM_RNG_BYTES_W(WB) (FFR_RNG_WORDS*FFR_TPB*(WB))
+#define FFR_SMEM_RNG_BYTES FFR_SMEM_RNG_BYTES_W(8)
 #ifndef FFR_DIRECT_MINB
 #define FFR_DIRECT_MINB 2
 #endif
 
-__device__ __forceinline__ void stage_blob(DevFlame *dst, const DevFlame *src, uint32_t bytes)
+__device__ __forceinline__ void stage_blob(void *dst, const void *src, uint32_t bytes)
 {
     const u64 *s = (const u64*)src;
     u64 *d = (u64*)dst;
@@ -58,6 +59,13 @@ __device__ __forceinline__ void stage_blob(DevFlame *dst, const DevFlame *src, u
         d[i] = s[i];
     __syncthreads();
 }
+
+/* (size_t)((pf - lo) * mult_d): truncating conversion, buffer_renderer.hpp:202 */
+__device__ __forceinline__ u64 to_index(double v) { return __double2ull_rz(v); }
+__device__ __forceinline__ u64 to_index(float v) { return __float2ull_rz(v); }
+/* ++hist (buffer_renderer.hpp:211-215) for u64 / u32 counters */
+__device__ __forceinline__ void hist_add(u64 *cell, unsigned n) { atomicAdd(cell,(u64)n); }
+__device__ __forceinline__ void hist_add(unsigned int *cell, unsigned n) { atomicAdd(cell,n); }
 
 /* add the 16-bit per-xform selection counters packed in pk0/pk1 to the block's counters */
 __device__ __forceinline__ void flush_packed(unsigned long long *s_xf, u64 &pk0, u64 &pk1)
@@ -77,30 +85,30 @@ __device__ __forceinline__ void flush_packed(unsigned long long *s_xf, u64 &pk0,
 #define FOR_COLOR(i) _Pragma("unroll") \
     for (int i = 0; i < (RCAP <= 4 ? RCAP : (int)r); ++i) if (RCAP > 4 || i < (int)r)
 
-template <int D, int RCAP> struct ChainState
+template <typename T, int D, int RCAP> struct ChainState
 {
-    Rng rng;
-    double p[D];
-    double c[RCAP > 0 ? RCAP : 1];
+    RngT<T> rng;
+    T p[D];
+    T c[RCAP > 0 ? RCAP : 1];
 };
 
 /* cold path, kept out of line and by value: RenderIterator::init() after a bad value
    (render_iterator.hpp:52-60 via buffer_renderer.hpp:185) */
-template <int D, int RCAP, bool AFFINE_ONLY>
-__device__ __noinline__ ChainState<D,RCAP> chain_reinit(const DevFlame *fl, Rng rng)
+template <typename T, int D, int RCAP, bool AFFINE_ONLY>
+__device__ __noinline__ ChainState<T,D,RCAP> chain_reinit(const DevFlameT<T> *fl, RngT<T> rng)
 {
-    ChainState<D,RCAP> st;
-    const DevXForm *xfs = blob_xforms(fl);
-    const DevVar *vars = blob_vars(fl);
+    ChainState<T,D,RCAP> st;
+    const DevXFormT<T> *xfs = blob_xforms(fl);
+    const DevVarT<T> *vars = blob_vars(fl);
     const uint32_t r = fl->r;
-    double p[D];
+    T p[D];
 #pragma unroll
     for (int i = 0; i < D; ++i)
         p[i] = 2.0*rng.num() - 1.0;
-    for (int s = 0; s < FFR_SETTLE_ITERS; ++s)
+    for (int s = 0; s < Real<T>::settle_iters; ++s)
     {
         uint32_t xi = select_xform(fl,rng);
-        xform_apply<D,AFFINE_ONLY>(xfs[xi],vars,rng,p,p);
+        xform_apply<T,D,AFFINE_ONLY>(xfs[xi],vars,rng,p,p);
     }
     FOR_COLOR(i)
         st.c[i] = rng.num();
@@ -111,30 +119,31 @@ __device__ __noinline__ ChainState<D,RCAP> chain_reinit(const DevFlame *fl, Rng 
     return st;
 }
 
-template <int D, int RCAP, bool AFFINE_ONLY>
+template <typename T, int D, int RCAP, bool AFFINE_ONLY>
 __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) render_kernel(const RenderParams prm)
 {
+    typedef typename Real<T>::word W;   /* generator word == histogram counter type */
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned int s_group;
-    u64 *rng_base = (u64*)smem;
-    DevFlame *fl = (DevFlame*)(smem + FFR_SMEM_RNG_BYTES);
+    W *rng_base = (W*)smem;
+    DevFlameT<T> *fl = (DevFlameT<T>*)(smem + FFR_SMEM_RNG_BYTES_W(sizeof(W)));
     stage_blob(fl,prm.blob,prm.blob_bytes);
 
-    const DevXForm *xfs = blob_xforms(fl);
-    const DevVar *vars = blob_vars(fl);
+    const DevXFormT<T> *xfs = blob_xforms(fl);
+    const DevVarT<T> *vars = blob_vars(fl);
     const uint32_t nx = fl->num_xforms;
     const uint32_t r = fl->r;
     const uint32_t cellsz = fl->cell;
     const bool has_final = fl->has_final;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const double *__restrict__ colors = prm.colors;
-    u64 *__restrict__ buffer = prm.buffer;
+    const T *__restrict__ colors = (const T*)prm.colors;
+    W *__restrict__ buffer = (W*)prm.buffer;
     const bool warp_agg = prm.scatter_mode == FFR_SCATTER_WARP_AGG;
     const bool discard = prm.scatter_mode == FFR_SCATTER_DISCARD || prm.scatter_mode == FFR_SCATTER_TRACE;
     u64 *__restrict__ trace = prm.scatter_mode == FFR_SCATTER_TRACE ? prm.trace : nullptr;
 
-    Rng rng;
+    RngT<T> rng;
     rng.bind(rng_base,tid);
     rng.a = rng.b = rng.c = 0;
     rng.cnt = 0;
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
     if (tid < 8)
         s_xf[tid] = 0;
     __syncthreads();
-    double pmin[D], pmax[D];
+    T pmin[D], pmax[D];
 #pragma unroll
     for (int i = 0; i < D; ++i)
     {
@@ -181,8 +190,8 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
         /* rng::setSeed((u64)seed_k) */
         rng.seed(splitmix64(prm.base_seed + prm.chain_first + kk));
 
-        double p[D], pf[D];
-        double c[RCAP > 0 ? RCAP : 1], cf[RCAP > 0 ? RCAP : 1];
+        T p[D], pf[D];
+        T c[RCAP > 0 ? RCAP : 1], cf[RCAP > 0 ? RCAP : 1];
         bool dead = false;
         /* RenderIterator::_init: p = randPoint (flame_rng.hpp:151-158) */
 #pragma unroll
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
 
         /* iterations -53..-1 are the settle iterations of _init (no stats, no plotting);
            sharing the loop keeps one inlined copy of the xform interpreter */
-        for (int it = -FFR_SETTLE_ITERS; it < chain_len; ++it)
+        for (int it = -Real<T>::settle_iters; it < chain_len; ++it)
         {
             if (it == 0 && RCAP > 0)
             {
@@ -204,25 +213,25 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
             {
                 /* RenderIterator::iterate, render_iterator.hpp:106-139 */
                 xi = select_xform(fl,rng);
-                const DevXForm &xf = xfs[xi];
-                xform_apply<D,AFFINE_ONLY>(xf,vars,rng,p,p);
+                const DevXFormT<T> &xf = xfs[xi];
+                xform_apply<T,D,AFFINE_ONLY>(xf,vars,rng,p,p);
                 if (it >= 0)
                 {
                     if (RCAP > 0 && (xf.flags & XF_HAS_COLOR))
                     {
-                        const double s = xf.color_speed;
+                        const T s = xf.color_speed;
                         FOR_COLOR(i)
                             c[i] = (1.0-s)*c[i] + s*__ldg(colors + xf.color_off + i);
                     }
                     if (has_final)
                     {
-                        const DevXForm &xff = xfs[nx];
-                        xform_apply<D,AFFINE_ONLY>(xff,vars,rng,p,pf);
+                        const DevXFormT<T> &xff = xfs[nx];
+                        xform_apply<T,D,AFFINE_ONLY>(xff,vars,rng,p,pf);
                         if (RCAP > 0)
                         {
                             if (xff.flags & XF_HAS_COLOR)
                             {
-                                const double s = xff.color_speed;
+                                const T s = xff.color_speed;
                                 FOR_COLOR(i)
                                     cf[i] = (1.0-s)*c[i] + s*__ldg(colors + xff.color_off + i);
                             }
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
                             prm.stats->bad_xf[idx] = xf.json_id;
 #pragma unroll
                             for (int i = 0; i < D; ++i)
-                                prm.stats->bad_pt[idx][i] = p[i];
+                                prm.stats->bad_pt[idx][i] = (double)p[i];
                         }
                         if (idx + 1 > prm.bv_limit)
                         {
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
                         else
                         {
                             /* iter.init(): pf, cf keep their stale values */
-                            ChainState<D,RCAP> st = chain_reinit<D,RCAP,AFFINE_ONLY>(fl,rng);
+                            ChainState<T,D,RCAP> st = chain_reinit<T,D,RCAP,AFFINE_ONLY>(fl,rng);
                             rng = st.rng;
 #pragma unroll
                             for (int i = 0; i < D; ++i)
@@ -294,26 +303,26 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
                         {
                             ++n_plot;
                             /* :202-209: truncating double -> index per dimension */
-                            u64 bi = __double2ull_rz((pf[0] - fl->lo[0]) * fl->mult_d[0]);
+                            u64 bi = to_index((pf[0] - fl->lo[0]) * fl->mult_d[0]);
 #pragma unroll
                             for (int i = 1; i < D; ++i)
-                                bi += __double2ull_rz((pf[i] - fl->lo[i]) * fl->mult_d[i]) * fl->mult_i[i];
+                                bi += to_index((pf[i] - fl->lo[i]) * fl->mult_d[i]) * fl->mult_i[i];
                             if (trace)
                                 trace[(u64)it*prm.chain_count + kk] = bi;
-                            u64 *cell = buffer + bi*cellsz;
+                            W *cell = buffer + bi*cellsz;
                             if (warp_agg)
                             {
                                 /* hits of colliding lanes are merged before they leave the SM */
                                 const unsigned peers = __match_any_sync(__activemask(),bi);
                                 if ((int)(__ffs(peers) - 1) == lane)
-                                    atomicAdd(cell,(u64)__popc(peers));
+                                    hist_add(cell,(unsigned)__popc(peers));
                             }
                             else if (!discard)
-                                atomicAdd(cell,1ULL); /* :211-215 */
+                                hist_add(cell,1u); /* :211-215 */
                             if (RCAP > 0 && !discard)
                             {
                                 FOR_COLOR(i) /* :217-229 */
-                                    atomicAdd((double*)(cell + 1 + i),cf[i]);
+                                    atomicAdd((T*)(cell + 1 + i),cf[i]);
                             }
                         }
                     }
@@ -365,8 +374,8 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
 #pragma unroll
         for (int i = 0; i < D; ++i)
         {
-            double a = __shfl_xor_sync(0xffffffffu,pmin[i],o);
-            double b = __shfl_xor_sync(0xffffffffu,pmax[i],o);
+            T a = __shfl_xor_sync(0xffffffffu,pmin[i],o);
+            T b = __shfl_xor_sync(0xffffffffu,pmax[i],o);
             pmin[i] = (a < pmin[i]) ? a : pmin[i];
             pmax[i] = (b > pmax[i]) ? b : pmax[i];
         }
@@ -378,8 +387,8 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
 #pragma unroll
         for (int i = 0; i < D; ++i)
         {
-            atomicMin(&prm.stats->pt_min[i],f64_to_ordered(pmin[i]));
-            atomicMax(&prm.stats->pt_max[i],f64_to_ordered(pmax[i]));
+            atomicMin(&prm.stats->pt_min[i],f64_to_ordered((double)pmin[i]));
+            atomicMax(&prm.stats->pt_max[i],f64_to_ordered((double)pmax[i]));
         }
     }
 }
@@ -399,27 +408,28 @@ __global__ void __launch_bounds__(FFR_TPB,AFFINE_ONLY ? 3 : FFR_DIRECT_MINB) ren
 #define FFR_REGROUP_MINB 2
 #endif
 
-template <int D, int RCAP>
+template <typename T, int D, int RCAP>
 __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regroup(const RenderParams prm)
 {
+    typedef typename Real<T>::word W;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned int s_group;
     __shared__ unsigned int s_xi[FFR_TPB];
     __shared__ unsigned short s_perm[FFR_TPB];
     __shared__ unsigned int s_wcnt[FFR_NWARPS][32];
-    u64 *rng_base = (u64*)smem;                      /* randmem columns only (16 words/slot) */
-    u64 *rsl_base = prm.rsl_scratch + (size_t)blockIdx.x*16*FFR_TPB; /* randrsl: L2-resident */
-    u64 *st_a = rng_base + 16*FFR_TPB;               /* randa, randb, randc, randcnt per slot */
-    u64 *st_b = st_a + FFR_TPB;
-    u64 *st_c = st_b + FFR_TPB;
-    u64 *st_n = st_c + FFR_TPB;
-    double *sp = (double*)(st_n + FFR_TPB);          /* p[d][slot] */
-    double *sc = sp + D*FFR_TPB;                     /* c[i][slot], RCAP rows */
-    DevFlame *fl = (DevFlame*)(sc + RCAP*FFR_TPB);
+    W *rng_base = (W*)smem;                          /* randmem columns only (16 words/slot) */
+    W *rsl_base = (W*)prm.rsl_scratch + (size_t)blockIdx.x*16*FFR_TPB; /* randrsl: L2-resident */
+    W *st_a = rng_base + 16*FFR_TPB;                 /* randa, randb, randc, randcnt per slot */
+    W *st_b = st_a + FFR_TPB;
+    W *st_c = st_b + FFR_TPB;
+    W *st_n = st_c + FFR_TPB;
+    T *sp = (T*)(st_n + FFR_TPB);                    /* p[d][slot] */
+    T *sc = sp + D*FFR_TPB;                          /* c[i][slot], RCAP rows */
+    DevFlameT<T> *fl = (DevFlameT<T>*)(sc + RCAP*FFR_TPB);
     stage_blob(fl,prm.blob,prm.blob_bytes);
 
-    const DevXForm *xfs = blob_xforms(fl);
-    const DevVar *vars = blob_vars(fl);
+    const DevXFormT<T> *xfs = blob_xforms(fl);
+    const DevVarT<T> *vars = blob_vars(fl);
     const uint32_t nx = fl->num_xforms;
     const uint32_t r = fl->r;
     const uint32_t cellsz = fl->cell;
@@ -427,15 +437,15 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const double *__restrict__ colors = prm.colors;
-    u64 *__restrict__ buffer = prm.buffer;
+    const T *__restrict__ colors = (const T*)prm.colors;
+    W *__restrict__ buffer = (W*)prm.buffer;
     const bool warp_agg = prm.scatter_mode == FFR_SCATTER_WARP_AGG;
     const bool discard = prm.scatter_mode == FFR_SCATTER_DISCARD || prm.scatter_mode == FFR_SCATTER_TRACE;
     u64 *__restrict__ trace = prm.scatter_mode == FFR_SCATTER_TRACE ? prm.trace : nullptr;
 
     u64 n_iter = 0, n_plot = 0;
     u64 xfc = 0;             /* warp 0, lane k: selections of xform k */
-    double pmin[D], pmax[D];
+    T pmin[D], pmax[D];
 #pragma unroll
     for (int i = 0; i < D; ++i)
     {
@@ -449,7 +459,7 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
 #define LOAD_RNG(R,slot) do { (R).col = rng_base + (slot); (R).rcol = rsl_base + (slot); (R).a = st_a[slot]; (R).b = st_b[slot]; \
         (R).c = st_c[slot]; (R).cnt = (int)st_n[slot]; } while (0)
 #define STORE_RNG(R,slot) do { st_a[slot] = (R).a; st_b[slot] = (R).b; st_c[slot] = (R).c; \
-        st_n[slot] = (u64)(R).cnt; } while (0)
+        st_n[slot] = (W)(R).cnt; } while (0)
 
     for (;;)
     {
@@ -467,7 +477,7 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
             ((kk+1 == prm.chain_count && prm.last_len) ? (int)prm.last_len : chain_len);
         bool dead = false;   /* owner-side flag of slot tid */
         {
-            Rng rng;
+            RngT<T> rng;
             rng.col = rng_base + tid;
             rng.rcol = rsl_base + tid;
             rng.seed(splitmix64(prm.base_seed + prm.chain_first + kk));
@@ -478,10 +488,10 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
         }
         s_xi[tid] = 0;
 
-        for (int it = -FFR_SETTLE_ITERS; it < chain_len; ++it)
+        for (int it = -Real<T>::settle_iters; it < chain_len; ++it)
         {
             /* ---- A: owner draws ---- */
-            Rng rng;
+            RngT<T> rng;
             LOAD_RNG(rng,tid);
             if (it == 0 && RCAP > 0)
             {
@@ -534,20 +544,20 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
             const uint32_t xi = s_xi[s];
             if (xi < nx)
             {
-                const DevXForm &xf = xfs[xi];
-                double p[D], pf[D];
-                double c[RCAP > 0 ? RCAP : 1], cf[RCAP > 0 ? RCAP : 1];
+                const DevXFormT<T> &xf = xfs[xi];
+                T p[D], pf[D];
+                T c[RCAP > 0 ? RCAP : 1], cf[RCAP > 0 ? RCAP : 1];
 #pragma unroll
                 for (int i = 0; i < D; ++i)
                     p[i] = sp[i*FFR_TPB + s];
-                Rng wr;
+                RngT<T> wr;
                 wr.col = rng_base + s;
                 wr.rcol = rsl_base + s;
                 const bool xr = (xf.flags & XF_USES_RNG) || (it >= 0 && has_final && (xfs[nx].flags & XF_USES_RNG));
                 if (xr)
                     LOAD_RNG(wr,s);
                 /* RenderIterator::iterate, render_iterator.hpp:106-139 */
-                xform_apply<D,false>(xf,vars,wr,p,p);
+                xform_apply<T,D,false>(xf,vars,wr,p,p);
                 if (it >= 0)
                 {
                     if (RCAP > 0)
@@ -556,20 +566,20 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
                             c[i] = sc[i*FFR_TPB + s];
                         if (xf.flags & XF_HAS_COLOR)
                         {
-                            const double cs = xf.color_speed;
+                            const T cs = xf.color_speed;
                             FOR_COLOR(i)
                                 c[i] = (1.0-cs)*c[i] + cs*__ldg(colors + xf.color_off + i);
                         }
                     }
                     if (has_final)
                     {
-                        const DevXForm &xff = xfs[nx];
-                        xform_apply<D,false>(xff,vars,wr,p,pf);
+                        const DevXFormT<T> &xff = xfs[nx];
+                        xform_apply<T,D,false>(xff,vars,wr,p,pf);
                         if (RCAP > 0)
                         {
                             if (xff.flags & XF_HAS_COLOR)
                             {
-                                const double cs = xff.color_speed;
+                                const T cs = xff.color_speed;
                                 FOR_COLOR(i)
                                     cf[i] = (1.0-cs)*c[i] + cs*__ldg(colors + xff.color_off + i);
                             }
@@ -606,7 +616,7 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
                             prm.stats->bad_xf[idx] = xf.json_id;
 #pragma unroll
                             for (int i = 0; i < D; ++i)
-                                prm.stats->bad_pt[idx][i] = p[i];
+                                prm.stats->bad_pt[idx][i] = (double)p[i];
                         }
                         if (idx + 1 > prm.bv_limit)
                         {
@@ -619,7 +629,7 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
                             /* iter.init() on the slot's own stream; pf, cf stay stale (Q3) */
                             if (!xr)
                                 LOAD_RNG(wr,s);
-                            ChainState<D,RCAP> st = chain_reinit<D,RCAP,false>(fl,wr);
+                            ChainState<T,D,RCAP> st = chain_reinit<T,D,RCAP,false>(fl,wr);
                             wr = st.rng;
                             STORE_RNG(wr,s);
 #pragma unroll
@@ -651,25 +661,25 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
                         if (inb)
                         {
                             ++n_plot;
-                            u64 bi = __double2ull_rz((pf[0] - fl->lo[0]) * fl->mult_d[0]);
+                            u64 bi = to_index((pf[0] - fl->lo[0]) * fl->mult_d[0]);
 #pragma unroll
                             for (int i = 1; i < D; ++i)
-                                bi += __double2ull_rz((pf[i] - fl->lo[i]) * fl->mult_d[i]) * fl->mult_i[i];
+                                bi += to_index((pf[i] - fl->lo[i]) * fl->mult_d[i]) * fl->mult_i[i];
                             if (trace)
                                 trace[(u64)it*prm.chain_count + (g*FFR_TPB + s)] = bi;
-                            u64 *cell = buffer + bi*cellsz;
+                            W *cell = buffer + bi*cellsz;
                             if (warp_agg)
                             {
                                 const unsigned pe = __match_any_sync(__activemask(),bi);
                                 if ((int)(__ffs(pe) - 1) == lane)
-                                    atomicAdd(cell,(u64)__popc(pe));
+                                    hist_add(cell,(unsigned)__popc(pe));
                             }
                             else if (!discard)
-                                atomicAdd(cell,1ULL);
+                                hist_add(cell,1u);
                             if (RCAP > 0 && !discard)
                             {
                                 FOR_COLOR(i)
-                                    atomicAdd((double*)(cell + 1 + i),cf[i]);
+                                    atomicAdd((T*)(cell + 1 + i),cf[i]);
                             }
                         }
                     }
@@ -697,8 +707,8 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
 #pragma unroll
         for (int i = 0; i < D; ++i)
         {
-            double a = __shfl_xor_sync(0xffffffffu,pmin[i],o);
-            double b = __shfl_xor_sync(0xffffffffu,pmax[i],o);
+            T a = __shfl_xor_sync(0xffffffffu,pmin[i],o);
+            T b = __shfl_xor_sync(0xffffffffu,pmax[i],o);
             pmin[i] = (a < pmin[i]) ? a : pmin[i];
             pmax[i] = (b > pmax[i]) ? b : pmax[i];
         }
@@ -710,34 +720,44 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
 #pragma unroll
         for (int i = 0; i < D; ++i)
         {
-            atomicMin(&prm.stats->pt_min[i],f64_to_ordered(pmin[i]));
-            atomicMax(&prm.stats->pt_max[i],f64_to_ordered(pmax[i]));
+            atomicMin(&prm.stats->pt_min[i],f64_to_ordered((double)pmin[i]));
+            atomicMax(&prm.stats->pt_max[i],f64_to_ordered((double)pmax[i]));
         }
     }
 }
 
-#define FFR_SMEM_REGROUP_BYTES(D,RCAP) (16*FFR_TPB*8 + 4*FFR_TPB*8 + (D)*FFR_TPB*8 + (RCAP)*FFR_TPB*8)
+#define FFR_SMEM_REGROUP_BYTES(D,RCAP,EB) ((16 + 4 + (D) + (RCAP))*FFR_TPB*(EB))
 
-/* K2: dst += src with the reference's mixed element typing: element 0 of each cell is a u64
-   count, elements 1..r are f64 colour sums (buffer_renderer.hpp:375-391). src may be peer
-   memory (multi-GPU reduce over NVLink) or a staged host buffer (-i). */
-__global__ void add_buffer_kernel(u64 *__restrict__ dst, const u64 *__restrict__ src, u64 n_elems,
-        uint32_t cellsz)
+/* K2: dst += src with the reference's mixed element typing: element 0 of each cell is a
+   count (u64 / u32), elements 1..r are colour sums (f64 / f32) (buffer_renderer.hpp:375-391).
+   src may be peer memory (multi-GPU reduce over NVLink) or a staged host buffer (-i). */
+template <typename T>
+__global__ void add_buffer_kernel(typename Real<T>::word *__restrict__ dst,
+        const typename Real<T>::word *__restrict__ src, u64 n_elems, uint32_t cellsz)
 {
+    typedef typename Real<T>::word W;
     const u64 stride = (u64)gridDim.x*blockDim.x;
     for (u64 i = (u64)blockIdx.x*blockDim.x + threadIdx.x; i < n_elems; i += stride)
     {
-        const u64 s = src[i];
+        const W s = src[i];
         if (cellsz == 1 || i % cellsz == 0)
             dst[i] += s;
         else
-            dst[i] = (u64)__double_as_longlong(__longlong_as_double((long long)dst[i])
-                + __longlong_as_double((long long)s));
+        {
+            T a, b;
+            W d = dst[i];
+            memcpy(&a,&d,sizeof(T));
+            memcpy(&b,&s,sizeof(T));
+            a += b;
+            memcpy(&d,&a,sizeof(T));
+            dst[i] = d;
+        }
     }
 }
 
 /* K3: histogramSum / histogramMax, buffer_renderer.hpp:483-509 */
-__global__ void hist_sum_max_kernel(const u64 *__restrict__ buf, u64 cells, uint32_t cellsz,
+template <typename W>
+__global__ void hist_sum_max_kernel(const W *__restrict__ buf, u64 cells, uint32_t cellsz,
         u64 *out_sum, u64 *out_max)
 {
     u64 sum = 0, mx = 0;
@@ -764,7 +784,8 @@ __global__ void hist_sum_max_kernel(const u64 *__restrict__ buf, u64 cells, uint
 
 /* K4a: histogram min/max for the tone map (ImageRenderer::getValueBounds,
    image_renderer.hpp:112-127, with func = count) */
-__global__ void hist_min_max_kernel(const u64 *__restrict__ buf, u64 cells, uint32_t cellsz,
+template <typename W>
+__global__ void hist_min_max_kernel(const W *__restrict__ buf, u64 cells, uint32_t cellsz,
         u64 *out_min, u64 *out_max)
 {
     u64 mn = ~0ULL, mx = 0;
@@ -790,49 +811,54 @@ __global__ void hist_min_max_kernel(const u64 *__restrict__ buf, u64 cells, uint
     }
 }
 
-/* K4b: log-density tone map, one thread per cell, coalesced: reads (1+r)*8 B, writes
-   channels*bits/8 B per cell (HBM bound). Pixel math of render_image, src/ffr_img.cpp:
+/* K4b: log-density tone map, one thread per cell, coalesced: reads (1+r)*sizeof(T) B, writes
+   channels*bits/8 B per cell (HBM bound). Pixel math of render_image, src/ffr_img.cpp, in
+   num_t arithmetic (std::log / std::pow pick the float overloads in the float build):
      gray  l = log(1+n)/max; v = pow(l,1/gamma); pix = (pix_t)(v*pix_scale)      :236-243
      rgb   v * colour_i/n per channel                                            :283-294
      mono  n != 0 ? 1 : 0                                                        :259-263
-   pix_scale = 2^bits * (1 - 2^-52) (constants.hpp:77-91). `max` = log(1 + hist_max) evaluated
-   with the SAME device log as the cells so the brightest cell maps to exactly 1.0 as in the
-   reference (log is monotonic, so this equals the max over cells of log(1+n)). Cells with
-   n == 0 in RGB mode are NaN in the reference (0/0, then an undefined cast that yields 0 on
-   x86-64): they are 0 here. Values are clamped to the top code instead of wrapping. */
-template <typename PIX>
-__global__ void tonemap_kernel(const u64 *__restrict__ buf, u64 cells, uint32_t cellsz, int mode,
-        u64 hist_max, double gp, PIX *__restrict__ out)
+   pix_scale = 2^bits * (1 - machine eps) (constants.hpp:59-91). `max` = log(1 + hist_max)
+   evaluated with the SAME device log as the cells so the brightest cell maps to exactly 1.0 as
+   in the reference (log is monotonic, so this equals the max over cells of log(1+n)). Cells
+   with n == 0 in RGB mode are NaN in the reference (0/0, then an undefined cast that yields 0
+   on x86-64): they are 0 here. Values are clamped to the top code instead of wrapping. */
+template <typename T, typename PIX>
+__global__ void tonemap_kernel(const typename Real<T>::word *__restrict__ buf, u64 cells,
+        uint32_t cellsz, int mode, u64 hist_max, T gp, PIX *__restrict__ out)
 {
-    const double pix_scale = (double)(1ULL << (8*sizeof(PIX))) * (1.0 - 1.0/4503599627370496.0);
-    const double top = (double)((1ULL << (8*sizeof(PIX))) - 1);
-    const double mx = log(1 + (double)hist_max);
+    typedef typename Real<T>::word W;
+    const T adjust = sizeof(T) == 8 ? (T)(1.0 - 1.0/4503599627370496.0) : (T)(1.0f - 1.0f/8388608.0f);
+    const T pix_scale = (T)(1ULL << (8*sizeof(PIX))) * adjust;
+    const T top = (T)((1ULL << (8*sizeof(PIX))) - 1);
+    const T mx = log(1 + (T)hist_max);
     const u64 stride = (u64)gridDim.x*blockDim.x;
     for (u64 i = (u64)blockIdx.x*blockDim.x + threadIdx.x; i < cells; i += stride)
     {
-        const u64 *cell = buf + i*cellsz;
-        const u64 n = cell[0];
+        const W *cell = buf + i*cellsz;
+        const W n = cell[0];
         if (mode == FFR_TONE_MONO)
         {
-            out[i] = (PIX)((n != 0 ? 1.0 : 0.0) * pix_scale);
+            out[i] = (PIX)((n != 0 ? (T)1.0 : (T)0.0) * pix_scale);
             continue;
         }
-        const double l = log(1 + (double)n) / mx;
-        const double ll = pow(l,gp);
+        const T l = log(1 + (T)n) / mx;
+        const T ll = pow(l,gp);
         if (mode == FFR_TONE_GRAY)
         {
-            const double v = ll * pix_scale;
+            const T v = ll * pix_scale;
             out[i] = (PIX)(v > top ? top : v);
         }
         else
         {
-            const double h = (double)n;
+            const T h = (T)n;
 #pragma unroll
             for (int c = 0; c < 3; ++c)
             {
-                double v = (n == 0) ? 0.0
-                    : (ll * (__longlong_as_double((long long)cell[1+c]) / h)) * pix_scale;
-                v = v > top ? top : (v < 0.0 ? 0.0 : v);
+                T col;
+                const W bits = cell[1+c];
+                memcpy(&col,&bits,sizeof(T));
+                T v = (n == 0) ? (T)0.0 : (ll * (col / h)) * pix_scale;
+                v = v > top ? top : (v < (T)0.0 ? (T)0.0 : v);
                 out[i*3+c] = (PIX)v;
             }
         }
@@ -840,48 +866,53 @@ __global__ void tonemap_kernel(const u64 *__restrict__ buf, u64 cells, uint32_t 
 }
 
 /* T1: one XForm::applyIteration per point with its own seeded stream */
-template <int D>
-__global__ void __launch_bounds__(FFR_TPB) iterate_points_kernel(const DevFlame *blob,
+template <typename T, int D>
+__global__ void __launch_bounds__(FFR_TPB) iterate_points_kernel(const void *blob,
         uint32_t blob_bytes, int xf_slot, u64 n, const u64 *seeds, const double *pin, double *pout)
 {
+    typedef typename Real<T>::word W;
     extern __shared__ __align__(16) unsigned char smem[];
-    u64 *rng_base = (u64*)smem;
-    DevFlame *fl = (DevFlame*)(smem + FFR_SMEM_RNG_BYTES);
+    W *rng_base = (W*)smem;
+    DevFlameT<T> *fl = (DevFlameT<T>*)(smem + FFR_SMEM_RNG_BYTES_W(sizeof(W)));
     stage_blob(fl,blob,blob_bytes);
     const u64 i = (u64)blockIdx.x*FFR_TPB + threadIdx.x;
     if (i >= n)
         return;
-    Rng rng;
+    RngT<T> rng;
     rng.bind(rng_base,threadIdx.x);
     rng.seed(seeds[i]);
-    double p[D];
+    T p[D];
 #pragma unroll
     for (int d = 0; d < D; ++d)
-        p[d] = pin[i*D+d];
-    xform_apply<D,false>(blob_xforms(fl)[xf_slot],blob_vars(fl),rng,p,p);
+        p[d] = (T)pin[i*D+d];
+    xform_apply<T,D,false>(blob_xforms(fl)[xf_slot],blob_vars(fl),rng,p,p);
 #pragma unroll
     for (int d = 0; d < D; ++d)
-        pout[i*D+d] = p[d];
+        pout[i*D+d] = (double)p[d];
 }
 
-/* T1: raw ISAAC stream */
+/* T1: raw ISAAC stream (words widened to u64) */
+template <typename T>
 __global__ void __launch_bounds__(FFR_TPB) isaac_words_kernel(u64 seed, u64 n, u64 *out)
 {
+    typedef typename Real<T>::word W;
     extern __shared__ __align__(16) unsigned char smem[];
-    Rng rng;
-    rng.bind((u64*)smem,threadIdx.x);
+    RngT<T> rng;
+    rng.bind((W*)smem,threadIdx.x);
     rng.seed(seed + threadIdx.x);
     if (threadIdx.x == 0)
         for (u64 i = 0; i < n; ++i)
-            out[i] = rng.next();
+            out[i] = (u64)rng.next();
 }
 
 /* M1b: attractor replay: the same RED mix at the cell indices a render of this flame produced
    (FFR_SCATTER_TRACE), thread k replaying chain k in order, so warps collide on hot cells
    exactly as the render's warps do -- the measured scatter roofline for THIS access pattern. */
-__global__ void __launch_bounds__(FFR_TPB) atomic_replay_kernel(u64 *buffer, const u64 *__restrict__ trace,
-        u64 chain_count, u64 chain_len, uint32_t cellsz)
+template <typename T>
+__global__ void __launch_bounds__(FFR_TPB) atomic_replay_kernel(typename Real<T>::word *buffer,
+        const u64 *__restrict__ trace, u64 chain_count, u64 chain_len, uint32_t cellsz)
 {
+    typedef typename Real<T>::word W;
     const u64 k = (u64)blockIdx.x*blockDim.x + threadIdx.x;
     if (k >= chain_count)
         return;
@@ -890,18 +921,20 @@ __global__ void __launch_bounds__(FFR_TPB) atomic_replay_kernel(u64 *buffer, con
         const u64 bi = trace[it*chain_count + k];
         if (bi == ~0ULL)
             continue;
-        u64 *cell = buffer + bi*cellsz;
-        atomicAdd(cell,1ULL);
+        W *cell = buffer + bi*cellsz;
+        hist_add(cell,1u);
         for (uint32_t i = 1; i < cellsz; ++i)
-            atomicAdd((double*)(cell + i),0.5);
+            atomicAdd((T*)(cell + i),(T)0.5);
     }
 }
 
-/* M1: random-atomic microbenchmark: same RED mix as the render kernel's scatter (1 u64 +
-   r f64 per cell) at uniformly random cells, no chaos game in front of it. */
-__global__ void __launch_bounds__(FFR_TPB) atomic_bench_kernel(u64 *buffer, u64 cells,
+/* M1: random-atomic microbenchmark: same RED mix as the render kernel's scatter (1 count +
+   r colour sums per cell) at uniformly random cells, no chaos game in front of it. */
+template <typename T>
+__global__ void __launch_bounds__(FFR_TPB) atomic_bench_kernel(typename Real<T>::word *buffer, u64 cells,
         uint32_t cellsz, u64 per_thread, u64 seed)
 {
+    typedef typename Real<T>::word W;
     u64 s = splitmix64(seed + (u64)blockIdx.x*blockDim.x + threadIdx.x);
     for (u64 k = 0; k < per_thread; ++k)
     {
@@ -911,9 +944,9 @@ __global__ void __launch_bounds__(FFR_TPB) atomic_bench_kernel(u64 *buffer, u64 
         s ^= s >> 27;
         const u64 rnd = s * 0x2545F4914F6CDD1DULL;
         const u64 bi = __umul64hi(rnd,cells);
-        u64 *cell = buffer + bi*cellsz;
-        atomicAdd(cell,1ULL);
+        W *cell = buffer + bi*cellsz;
+        hist_add(cell,1u);
         for (uint32_t i = 1; i < cellsz; ++i)
-            atomicAdd((double*)(cell + i),0.5);
+            atomicAdd((T*)(cell + i),(T)0.5);
     }
 }

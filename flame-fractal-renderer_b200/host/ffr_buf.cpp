@@ -18,6 +18,8 @@ options:
 -z,--bad-values   number of bad values allowed before terminating render
    --seed         base seed of the per-chain ISAAC streams (default: clock)
    --gpus         number of GPUs to shard the chains over (default 1)
+   --float        the reference's float/uint32_t build (types.hpp:24-41) instead of the shipped
+                  double/uint64_t one: 4-byte buffer elements, ISAAC-32
 */
 
 #include "../../include/ffr_flame.h"
@@ -52,7 +54,8 @@ static void usage()
         "  -b [ --batch-size ] arg (=0)  batch size (samples per chain)\n"
         "  -z [ --bad-values ] arg (=256) bad values limit\n"
         "  --seed arg                    base seed (default: from the clock)\n"
-        "  --gpus arg (=1)               GPUs to use\n";
+        "  --gpus arg (=1)               GPUs to use\n"
+        "  --float                       float/uint32_t build (4-byte buffer elements)\n";
 }
 
 static bool read_all(std::istream& is, std::string& out)
@@ -92,6 +95,7 @@ int main(int argc, char **argv)
     uint64_t arg_seed = 0;
     bool have_seed = false;
     int arg_gpus = 1;
+    int arg_elem = 8;
 
     static const struct option longopts[] = {
         {"help",no_argument,nullptr,'h'},
@@ -104,6 +108,7 @@ int main(int argc, char **argv)
         {"bad-values",required_argument,nullptr,'z'},
         {"seed",required_argument,nullptr,1000},
         {"gpus",required_argument,nullptr,1001},
+        {"float",no_argument,nullptr,1002},
         {nullptr,0,nullptr,0}
     };
     if (argc < 2)
@@ -126,6 +131,7 @@ int main(int argc, char **argv)
         case 'z': arg_bad_values = strtoull(optarg,nullptr,10); break;
         case 1000: arg_seed = strtoull(optarg,nullptr,0); have_seed = true; break;
         case 1001: arg_gpus = atoi(optarg); break;
+        case 1002: arg_elem = 4; break;
         default: usage(); return 1;
         }
     }
@@ -190,7 +196,7 @@ int main(int argc, char **argv)
         }
     }
     char err[512];
-    ffr_flame *flame = ffr_flame_from_json(text.data(),text.size(),err,sizeof(err));
+    ffr_flame *flame = ffr_flame_from_json_ex(text.data(),text.size(),nullptr,0,arg_elem,err,sizeof(err));
     if (!flame)
     {
         std::cerr << "ERROR: " << err << std::endl;

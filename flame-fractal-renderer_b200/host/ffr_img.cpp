@@ -98,7 +98,8 @@ static void usage()
         "  -m [ --monochrome ]      binary image from histogram\n"
         "  -g [ --grayscale ]       grayscale image from histogram\n"
         "  -c [ --color ]           color image from 3d color only\n"
-        "  -b [ --bits ] arg (=8)   bits per color channel\n";
+        "  -b [ --bits ] arg (=8)   bits per color channel\n"
+        "  --float                  input buffers are from the float/uint32_t build\n";
 }
 
 int main(int argc, char **argv)
@@ -108,12 +109,14 @@ int main(int argc, char **argv)
     double arg_gamma = 1.0;
     size_t arg_bits = 8;
     bool arg_m = false, arg_g = false, arg_c = false;
+    int arg_elem = 8; /* --float: buffers of the float/uint32_t build */
     static const struct option longopts[] = {
         {"help",no_argument,nullptr,'h'}, {"flame",required_argument,nullptr,'f'},
         {"input",required_argument,nullptr,'i'}, {"output",required_argument,nullptr,'o'},
         {"gamma",required_argument,nullptr,'y'}, {"monochrome",no_argument,nullptr,'m'},
         {"grayscale",no_argument,nullptr,'g'}, {"color",no_argument,nullptr,'c'},
-        {"bits",required_argument,nullptr,'b'}, {nullptr,0,nullptr,0}
+        {"bits",required_argument,nullptr,'b'}, {"float",no_argument,nullptr,1002},
+        {nullptr,0,nullptr,0}
     };
     if (argc < 2)
     {
@@ -133,6 +136,7 @@ int main(int argc, char **argv)
         case 'g': arg_g = true; break;
         case 'c': arg_c = true; break;
         case 'b': arg_bits = strtoull(optarg,nullptr,10); break;
+        case 1002: arg_elem = 4; break;
         default: usage(); return 1;
         }
     }
@@ -177,7 +181,7 @@ int main(int argc, char **argv)
         text.assign(std::istreambuf_iterator<char>(f),std::istreambuf_iterator<char>());
     }
     char err[512];
-    ffr_flame *flame = ffr_flame_from_json(text.data(),text.size(),err,sizeof(err));
+    ffr_flame *flame = ffr_flame_from_json_ex(text.data(),text.size(),nullptr,0,arg_elem,err,sizeof(err));
     if (!flame)
     {
         std::cerr << "ERROR: " << err << std::endl;

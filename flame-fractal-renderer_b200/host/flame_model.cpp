@@ -24,9 +24,26 @@ namespace
 using ffr::Json;
 using ffr::JsonError;
 
-const double EPS = 1e-20;            // eps_v<double>, types/constants.hpp:21
-const double MAX_RECT = 1e10;        // max_rect_v<double>, constants.hpp:36
+// per-precision constants, types/constants.hpp:17-37. The reference is compiled for one
+// num_t (types.hpp:24-41); every constructor below runs in num_t arithmetic, so the whole
+// model is templated on T = num_t and the resulting values (exactly representable in a double)
+// are stored in the double fields of the POD desc.
+template <typename T> struct Consts;
+template <> struct Consts<double>
+{
+    static constexpr double eps = 1e-20;     // eps_v<double> :21
+    static constexpr double max_rect = 1e10; // max_rect_v<double> :36
+};
+template <> struct Consts<float>
+{
+    static constexpr float eps = 1e-10;      // eps_v<float> :19
+    static constexpr float max_rect = 1e5F;  // max_rect_v<float> :35
+};
 const uint64_t MAX_DIM = 65535;      // max_dim, constants.hpp:33
+
+// math::sincosg, utils/math.hpp:21-24
+inline void sincosg(float a, float& s, float& c) { sincosf(a,&s,&c); }
+inline void sincosg(double a, double& s, double& c) { sincos(a,&s,&c); }
 
 struct VarName { uint32_t op; const char *name; };
 
@@ -74,7 +91,8 @@ const VarName VAR_NAMES[] = {
 bool is2d(uint32_t op) { return op >= FFR_VAR_FIRST_2D && op <= FFR_VAR_LAST_2D; }
 
 // Point<T,N>(const Json&), types/point.hpp:59-77
-void parsePoint(const Json& j, uint32_t n, double *out)
+template <typename T>
+void parsePoint(const Json& j, uint32_t n, T *out)
 {
     if (!j.isArray())
         throw JsonError("Point(Json&): not an array");
@@ -85,21 +103,28 @@ void parsePoint(const Json& j, uint32_t n, double *out)
     for (uint32_t i = 0; i < n; ++i)
     {
         if (a[i].isInt())
-            out[i] = (double)a[i].intValue();
+            out[i] = (T)a[i].intValue();
         else if (a[i].isFloat())
-            out[i] = (double)a[i].floatValue();
+            out[i] = (T)a[i].floatValue();
         else
             throw JsonError("Point(Json&): entry is not a number");
     }
 }
 
 // Affine<T,N>::Affine(const Json&), types/affine.hpp:45-92
-void parseAffine(const Json& j, uint32_t n, double *A, double *b)
+template <typename T>
+void parseAffine(const Json& j, uint32_t n, double *Aout, double *bout)
 {
     if (!j.isObject())
         throw JsonError("Affine(Json&): not an object");
-    for (uint32_t i = 0; i < 9; ++i) A[i] = 0.0;
-    for (uint32_t i = 0; i < 3; ++i) b[i] = 0.0;
+    T A[9], b[3];
+    for (uint32_t i = 0; i < 9; ++i) A[i] = 0;
+    for (uint32_t i = 0; i < 3; ++i) b[i] = 0;
+    struct Store
+    {
+        T *A, *b; double *Ao, *bo;
+        ~Store() { for (int i = 0; i < 9; ++i) Ao[i] = A[i]; for (int i = 0; i < 3; ++i) bo[i] = b[i]; }
+    } store{A,b,Aout,bout};
     if (!j.has("A"))
     {
         for (uint32_t i = 0; i < n; ++i)
@@ -116,7 +141,7 @@ void parseAffine(const Json& j, uint32_t n, double *A, double *b)
         {
             try
             {
-                parsePoint(ja[i],n,A+i*n);
+                parsePoint<T>(ja[i],n,A+i*n);
             }
             catch (const std::exception& e)
             {
@@ -129,7 +154,7 @@ void parseAffine(const Json& j, uint32_t n, double *A, double *b)
     {
         try
         {
-            parsePoint(j["b"],n,b);
+            parsePoint<T>(j["b"],n,b);
         }
         catch (const std::exception& e)
         {
@@ -150,8 +175,10 @@ void identityAffine(uint32_t n, double *A, double *b)
 inline double F(const Json& j, const char *key) { return j[key].floatValue(); }
 
 // Variation<dims>::parseVariation and every constructor (variations.hpp)
+template <typename T>
 ffr_variation parseVariation(const Json& j, uint32_t D)
 {
+    const T EPS = Consts<T>::eps;
     std::string name = j["name"].stringValue();
     uint32_t op = ffr_var_op_from_name(name.c_str());
     // 2-d factory is empty below 2 dimensions (variations.hpp:2379-2384)
@@ -160,8 +187,10 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
     ffr_variation v;
     memset(&v,0,sizeof(v));
     v.op = op;
-    v.weight = j["weight"].floatValue(); // Variation ctor :45-48
-    double *p = v.params;
+    v.weight = (T)j["weight"].floatValue(); // Variation ctor :45-48 (num_t weight)
+    T p[FFR_MAX_VAR_PARAMS];
+    for (int i = 0; i < FFR_MAX_VAR_PARAMS; ++i) p[i] = 0;
+    // derived members are num_t; they are copied to the desc's double fields after the switch
     if (is2d(op) && D > 2) // VariationFrom2D ctor :72-88
     {
         int64_t ax = j["axis_x"].intValue();
@@ -183,46 +212,46 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
     switch (op)
     {
     case FFR_VAR_BENT: // :221-226
-        parsePoint(j["scales_neg"],D,p);
-        parsePoint(j["scales_pos"],D,p+4);
+        parsePoint<T>(j["scales_neg"],D,p);
+        parsePoint<T>(j["scales_pos"],D,p+4);
         break;
     case FFR_VAR_RECTANGLES: // :249-252
-        parsePoint(j["params"],D,p);
+        parsePoint<T>(j["params"],D,p);
         break;
     case FFR_VAR_FISHEYE: // :279-284
     case FFR_VAR_BUBBLE:  // :301-306
         p[0] = F(j,"addval");
         break;
     case FFR_VAR_SEPARATION: // :387-393
-        parsePoint(j["params"],D,p);
+        parsePoint<T>(j["params"],D,p);
         for (uint32_t i = 0; i < D; ++i)
             p[i] *= p[i];
-        parsePoint(j["inside"],D,p+4);
+        parsePoint<T>(j["inside"],D,p+4);
         break;
     case FFR_VAR_SPLITS: // :414-417
-        parsePoint(j["params"],D,p);
+        parsePoint<T>(j["params"],D,p);
         break;
     case FFR_VAR_MODULUS: // :455-460
-        parsePoint(j["params"],D,p);
+        parsePoint<T>(j["params"],D,p);
         for (uint32_t i = 0; i < D; ++i)
             p[i] *= 2.0;
         for (uint32_t i = 0; i < D; ++i)
             p[4+i] = 1.0/p[i];
         break;
     case FFR_VAR_CELLN: // :480-485
-        parsePoint(j["sizes"],D,p);
+        parsePoint<T>(j["sizes"],D,p);
         for (uint32_t i = 0; i < D; ++i)
             p[4+i] = 1.0 / p[i];
         break;
     case FFR_VAR_DISC2: // :629-643
     {
-        double rot = F(j,"rotation");
-        double twist = F(j,"twist");
+        T rot = F(j,"rotation");
+        T twist = F(j,"twist");
         p[0] = rot*M_PI;
-        double sinadd,cosadd;
-        sincos(twist,&sinadd,&cosadd);
+        T sinadd,cosadd;
+        sincosg((T)(twist),sinadd,cosadd);
         cosadd -= 1.0;
-        double k = 1.0 + twist;
+        T k = 1.0 + twist;
         if (twist > 2.0*M_PI) k -= 2.0*M_PI;
         if (twist < -2.0*M_PI) k += 2.0*M_PI;
         cosadd *= k;
@@ -239,22 +268,22 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
         break;
     case FFR_VAR_FAN: // :689-695
     {
-        double x = F(j,"x");
-        double y = F(j,"y");
+        T x = F(j,"x");
+        T y = F(j,"y");
         p[0] = M_PI * (x*x + EPS);
         p[1] = y;
         break;
     }
     case FFR_VAR_RINGS: // :718-722
     {
-        double val = F(j,"value");
+        T val = F(j,"value");
         p[0] = val*val + EPS;
         break;
     }
     case FFR_VAR_BLOB: // :879-886
     {
-        double low = F(j,"low");
-        double high = F(j,"high");
+        T low = F(j,"low");
+        T high = F(j,"high");
         p[0] = (high+low)/2.0;
         p[1] = (high-low)/2.0;
         p[2] = F(j,"waves");
@@ -269,7 +298,7 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
     case FFR_VAR_PERSPECTIVE: // :947-953
     {
         p[0] = F(j,"distance");
-        double angle = F(j,"angle");
+        T angle = F(j,"angle");
         p[1] = sin(angle);
         p[2] = p[0]*cos(angle);
         break;
@@ -277,8 +306,8 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
     case FFR_VAR_JULIAN:     // :971-978
     case FFR_VAR_JULIASCOPE: // :998-1005
     {
-        double power = F(j,"power");
-        double dist = F(j,"dist");
+        T power = F(j,"power");
+        T dist = F(j,"dist");
         p[0] = fabs(power);
         p[1] = 1.0/power;
         p[2] = dist/(2.0*power);
@@ -286,8 +315,8 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
     }
     case FFR_VAR_RADIAL_BLUR: // :1027-1032
     {
-        double angle = F(j,"angle");
-        sincos(angle*M_PI_2,&p[0],&p[1]);
+        T angle = F(j,"angle");
+        sincosg((T)(angle*M_PI_2),p[0],p[1]);
         p[2] = F(j,"flam3_weight");
         break;
     }
@@ -299,7 +328,7 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
         break;
     case FFR_VAR_NGON: // :1081-1089
     {
-        double sides = F(j,"sides");
+        T sides = F(j,"sides");
         p[0] = F(j,"power")/2.0;
         p[1] = (2.0*M_PI)/sides;
         p[2] = F(j,"corners");
@@ -330,10 +359,10 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
         p[1] = F(j,"flam3_weight");
         break;
     case FFR_VAR_MOBIUS: // :1609-1615
-        parsePoint(j["a"],2,p);
-        parsePoint(j["b"],2,p+2);
-        parsePoint(j["c"],2,p+4);
-        parsePoint(j["d"],2,p+6);
+        parsePoint<T>(j["a"],2,p);
+        parsePoint<T>(j["b"],2,p+2);
+        parsePoint<T>(j["c"],2,p+4);
+        parsePoint<T>(j["d"],2,p+6);
         break;
     case FFR_VAR_SPLIT: // :1659-1663
         p[0] = F(j,"xsize") * M_PI;
@@ -352,11 +381,11 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
         break;
     case FFR_VAR_WEDGE_JULIA: // :1733-1743
     {
-        double angle = F(j,"angle");
-        double count = F(j,"count");
-        double power = F(j,"power");
-        double invpower = 1.0/power;
-        double dist = F(j,"dist");
+        T angle = F(j,"angle");
+        T count = F(j,"count");
+        T power = F(j,"power");
+        T invpower = 1.0/power;
+        T dist = F(j,"dist");
         p[0] = dist/(2.0*power);
         p[1] = fabs(power);
         p[2] = invpower;
@@ -367,8 +396,8 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
     }
     case FFR_VAR_WEDGE_SPH: // :1765-1772
     {
-        double angle = F(j,"angle");
-        double count = F(j,"count");
+        T angle = F(j,"angle");
+        T count = F(j,"count");
         p[0] = F(j,"swirl");
         p[1] = count;
         p[3] = angle;
@@ -383,7 +412,7 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
         break;
     case FFR_VAR_SUPERSHAPE: // :1819-1828
     {
-        double n1 = F(j,"n1");
+        T n1 = F(j,"n1");
         p[0] = F(j,"m") / 4.0;
         p[1] = -1.0 / n1;
         p[2] = F(j,"n2");
@@ -418,9 +447,9 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
         break;
     case FFR_VAR_CPOW: // :2042-2050
     {
-        double r = F(j,"r");
-        double i = F(j,"i");
-        double power = F(j,"power");
+        T r = F(j,"r");
+        T i = F(j,"i");
+        T power = F(j,"power");
         p[3] = power;
         p[0] = 2.0*M_PI/power;
         p[1] = r/power;
@@ -431,8 +460,8 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
     {
         p[2] = F(j,"xamp");
         p[3] = F(j,"yamp");
-        double xlen = F(j,"xlen");
-        double ylen = F(j,"ylen");
+        T xlen = F(j,"xlen");
+        T ylen = F(j,"ylen");
         xlen *= xlen;
         ylen *= ylen;
         p[0] = 1.0 / std::max(EPS,xlen);
@@ -441,9 +470,9 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
     }
     case FFR_VAR_ESCHER: // :2153-2160
     {
-        double beta = F(j,"beta");
-        double seb,ceb;
-        sincos(beta,&seb,&ceb);
+        T beta = F(j,"beta");
+        T seb,ceb;
+        sincosg((T)(beta),seb,ceb);
         p[0] = 0.5*(1.0+ceb);
         p[1] = 0.5*seb;
         break;
@@ -462,7 +491,7 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
         break;
     case FFR_VAR_OSCOPE: // :2263-2270
     {
-        double freq = F(j,"frequency");
+        T freq = F(j,"frequency");
         p[0] = 2.0*M_PI*freq;
         p[1] = F(j,"amplitude");
         p[2] = F(j,"damping");
@@ -483,6 +512,8 @@ ffr_variation parseVariation(const Json& j, uint32_t D)
     default: // parameterless
         break;
     }
+    for (int i = 0; i < FFR_MAX_VAR_PARAMS; ++i)
+        v.params[i] = p[i];
     return v;
 }
 
@@ -494,8 +525,9 @@ struct XFormModel
 };
 
 // XForm<dims>::XForm, types/xform.hpp:71-172
+template <typename T>
 XFormModel parseXForm(const Json& in, uint64_t id, bool is_final, uint32_t D,
-        uint32_t color_dims, double default_color_speed)
+        uint32_t color_dims, T default_color_speed)
 {
     XFormModel m;
     memset(&m.x,0,sizeof(m.x));
@@ -504,7 +536,7 @@ XFormModel parseXForm(const Json& in, uint64_t id, bool is_final, uint32_t D,
     {
         try
         {
-            m.x.weight = in["weight"].floatValue();
+            m.x.weight = (T)in["weight"].floatValue();
         }
         catch (std::exception& e)
         {
@@ -521,7 +553,7 @@ XFormModel parseXForm(const Json& in, uint64_t id, bool is_final, uint32_t D,
     {
         try
         {
-            parseAffine(affine,D,m.x.pre_A,m.x.pre_b);
+            parseAffine<T>(affine,D,m.x.pre_A,m.x.pre_b);
         }
         catch (std::exception& e)
         {
@@ -535,7 +567,7 @@ XFormModel parseXForm(const Json& in, uint64_t id, bool is_final, uint32_t D,
     {
         try
         {
-            parseAffine(affine,D,m.x.post_A,m.x.post_b);
+            parseAffine<T>(affine,D,m.x.post_A,m.x.post_b);
         }
         catch (std::exception& e)
         {
@@ -547,7 +579,7 @@ XFormModel parseXForm(const Json& in, uint64_t id, bool is_final, uint32_t D,
     try
     {
         for (const Json& varj : in["variations"].arrayValue())
-            m.vars.push_back(parseVariation(varj,D));
+            m.vars.push_back(parseVariation<T>(varj,D));
     }
     catch (std::exception& e)
     {
@@ -564,7 +596,7 @@ XFormModel parseXForm(const Json& in, uint64_t id, bool is_final, uint32_t D,
             m.color.resize(color_dims);
             for (uint32_t i = 0; i < color_dims; ++i)
             {
-                m.color[i] = ca[i].floatValue();
+                m.color[i] = (T)ca[i].floatValue();
                 if (m.color[i] < 0.0 || m.color[i] > 1.0)
                     throw JsonError("color coordinate out of range");
             }
@@ -578,7 +610,7 @@ XFormModel parseXForm(const Json& in, uint64_t id, bool is_final, uint32_t D,
     {
         try
         {
-            m.x.color_speed = colorj.floatValue();
+            m.x.color_speed = (T)colorj.floatValue();
             if (m.x.color_speed < 0.0 || m.x.color_speed > 1.0)
                 throw JsonError("color speed out of range");
         }
@@ -629,6 +661,7 @@ namespace
 {
 
 // Flame<dims>::Flame(const Json&), types/flame.hpp:91-210
+template <typename T>
 ffr_flame *buildFlame(const Json& input)
 {
     std::unique_ptr<ffr_flame> fl(new ffr_flame);
@@ -640,7 +673,7 @@ ffr_flame *buildFlame(const Json& input)
         throw JsonError(std::to_string(dims) + "D not supported");
     uint32_t D = (uint32_t)dims;
     d.dims = D;
-    d.elem_size = 8;
+    d.elem_size = (uint32_t)sizeof(T);
     try
     {
         const auto& sizej = input["size"].arrayValue();
@@ -649,7 +682,7 @@ ffr_flame *buildFlame(const Json& input)
             throw JsonError("incorrect size length");
         if (boundsj.size() != D)
             throw JsonError("incorrect bounds length");
-        double M = MAX_RECT;
+        T M = Consts<T>::max_rect;
         for (uint32_t i = 0; i < D; ++i)
         {
             try
@@ -666,11 +699,11 @@ ffr_flame *buildFlame(const Json& input)
             const auto& boundj = boundsj[i].arrayValue();
             if (boundj.size() != 2)
                 throw JsonError("bounds[" + std::to_string(i) + "] wrong format");
-            double lo,hi;
+            T lo,hi;
             try
             {
-                lo = boundj[0].floatValue();
-                hi = boundj[1].floatValue();
+                lo = (T)boundj[0].floatValue();
+                hi = (T)boundj[1].floatValue();
             }
             catch (std::exception& e)
             {
@@ -700,7 +733,7 @@ ffr_flame *buildFlame(const Json& input)
         throw JsonError("Flame(): cannot parse xforms: " + std::string(e.what()));
     }
     uint64_t color_dims;
-    double color_speed;
+    T color_speed;
     Json cd,cs;
     try
     {
@@ -711,7 +744,7 @@ ffr_flame *buildFlame(const Json& input)
         if (color_dims > 127)
             throw JsonError("too many color dimensions");
         if (input.valueAt("color_speed",cs))
-            color_speed = cs.floatValue();
+            color_speed = (T)cs.floatValue();
         else
             color_speed = 0.5;
         if (color_speed < 0.0 || color_speed > 1.0)
@@ -727,7 +760,7 @@ ffr_flame *buildFlame(const Json& input)
     {
         try
         {
-            fl->models.push_back(parseXForm(xf,id,false,D,d.color_dims,color_speed));
+            fl->models.push_back(parseXForm<T>(xf,id,false,D,d.color_dims,color_speed));
         }
         catch (std::exception& e)
         {
@@ -742,7 +775,7 @@ ffr_flame *buildFlame(const Json& input)
     {
         try
         {
-            fl->final_model = parseXForm(fxf,FFR_FINAL_XFORM_ID,true,D,d.color_dims,color_speed);
+            fl->final_model = parseXForm<T>(fxf,FFR_FINAL_XFORM_ID,true,D,d.color_dims,color_speed);
         }
         catch (std::exception& e)
         {
@@ -761,13 +794,13 @@ ffr_flame *buildFlame(const Json& input)
     // Flame::_setupCumulativeWeights, flame.hpp:44-60
     size_t k = fl->models.size();
     fl->xfcw.assign(k,0.0);
-    double normdiv = 0.0;
+    T normdiv = 0.0;
     for (size_t i = 0; i < k; ++i)
-        normdiv += fl->models[i].x.weight;
-    double wsum = 0.0;
+        normdiv += (T)fl->models[i].x.weight;
+    T wsum = 0.0;
     for (size_t i = 0; i < k; ++i)
     {
-        wsum += fl->models[i].x.weight / normdiv;
+        wsum += (T)fl->models[i].x.weight / normdiv;
         fl->xfcw[i] = wsum;
     }
     fl->xfcw.back() = 1.0;
@@ -788,11 +821,13 @@ void setErr(char *err, size_t errlen, const std::string& msg)
 extern "C"
 {
 
-ffr_flame *ffr_flame_from_json_sized(const char *text, size_t len, const uint64_t *size,
-        int n_size, char *err, size_t errlen)
+ffr_flame *ffr_flame_from_json_ex(const char *text, size_t len, const uint64_t *size,
+        int n_size, int elem_size, char *err, size_t errlen)
 {
     try
     {
+        if (elem_size != 8 && elem_size != 4)
+            throw JsonError("elem_size must be 8 (double/uint64_t) or 4 (float/uint32_t)");
         Json j = Json::parse(text,len);
         if (size)
         {
@@ -801,7 +836,7 @@ ffr_flame *ffr_flame_from_json_sized(const char *text, size_t len, const uint64_
                 throw JsonError("size override length does not match dimensions");
             j.set("size",Json::makeArrayOfInts(size,(size_t)n_size));
         }
-        return buildFlame(j);
+        return elem_size == 8 ? buildFlame<double>(j) : buildFlame<float>(j);
     }
     catch (std::exception& e)
     {
@@ -810,9 +845,15 @@ ffr_flame *ffr_flame_from_json_sized(const char *text, size_t len, const uint64_
     }
 }
 
+ffr_flame *ffr_flame_from_json_sized(const char *text, size_t len, const uint64_t *size,
+        int n_size, char *err, size_t errlen)
+{
+    return ffr_flame_from_json_ex(text,len,size,n_size,8,err,errlen);
+}
+
 ffr_flame *ffr_flame_from_json(const char *text, size_t len, char *err, size_t errlen)
 {
-    return ffr_flame_from_json_sized(text,len,nullptr,0,err,errlen);
+    return ffr_flame_from_json_ex(text,len,nullptr,0,8,err,errlen);
 }
 
 const ffr_flame_desc *ffr_flame_get_desc(const ffr_flame *f)
@@ -828,14 +869,25 @@ void ffr_flame_free(ffr_flame *f)
 int ffr_flame_layout(const ffr_flame_desc *desc, double mult_d[FFR_MAX_DIMS],
         uint64_t mult_i[FFR_MAX_DIMS], uint64_t *cells, uint64_t *cell_size)
 {
-    // BufferRenderer::_init, buffer_renderer.hpp:114-140
-    const double scale_adjust_down = 1.0 - (double)(float)(1.0 / (double)(1L << 52)); // constants.hpp:28-29,61-62
+    // BufferRenderer::_init, buffer_renderer.hpp:114-140, in num_t arithmetic;
+    // scale_adjust_down_v<num_t> = 1 - emach (constants.hpp:25-30,59-62)
+    const bool f32 = desc->elem_size == 4;
     uint64_t n = 1;
     for (uint32_t i = 0; i < desc->dims; ++i)
     {
         uint64_t size = desc->size[i];
-        double m = (double)(size) / (desc->bounds_hi[i] - desc->bounds_lo[i]);
-        m *= scale_adjust_down;
+        double m;
+        if (f32)
+        {
+            float mf = (float)(size) / ((float)desc->bounds_hi[i] - (float)desc->bounds_lo[i]);
+            mf *= 1.0F - 1.0F / (float)(1 << 23);
+            m = mf;
+        }
+        else
+        {
+            m = (double)(size) / (desc->bounds_hi[i] - desc->bounds_lo[i]);
+            m *= 1.0 - (double)(float)(1.0 / (double)(1L << 52));
+        }
         if (mult_d) mult_d[i] = m;
         if (mult_i) mult_i[i] = n;
         n *= size;

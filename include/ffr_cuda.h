@@ -198,7 +198,9 @@ typedef struct ffr_flame_desc
 {
     uint32_t dims;             /* 1..3 */
     uint32_t color_dims;       /* r, 0..127 */
-    uint32_t elem_size;        /* sizeof(num_t)==sizeof(hist_t): 8 (double/u64, types.hpp:29,35) */
+    uint32_t elem_size;        /* sizeof(num_t)==sizeof(hist_t), types.hpp:24-41: 8 = double/uint64_t
+                                  (as shipped), 4 = float/uint32_t; every value of the desc must
+                                  then be exactly representable in that num_t */
     uint32_t has_final;
     uint64_t size[FFR_MAX_DIMS];
     double bounds_lo[FFR_MAX_DIMS];

@@ -31,6 +31,11 @@ ffr_flame *ffr_flame_from_json(const char *text, size_t len, char *err, size_t e
    examples; the reference has no setter, one edits the JSON). n_size must equal dims. */
 ffr_flame *ffr_flame_from_json_sized(const char *text, size_t len, const uint64_t *size,
         int n_size, char *err, size_t errlen);
+/* Same for either build of the reference: elem_size 8 = num_t double / hist_t uint64_t (as
+   shipped), 4 = float / uint32_t (types/types.hpp:24-41). All constructor arithmetic runs in
+   that num_t; size may be NULL. */
+ffr_flame *ffr_flame_from_json_ex(const char *text, size_t len, const uint64_t *size,
+        int n_size, int elem_size, char *err, size_t errlen);
 const ffr_flame_desc *ffr_flame_get_desc(const ffr_flame *f);
 void ffr_flame_free(ffr_flame *f);
 

@@ -19,17 +19,18 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_LIB = os.path.join(_HERE, "libffr_oracle.so")
 REF_LIB = os.path.join(_HERE, "_ref", "libffr_ref.so")
+REF_LIB_F32 = os.path.join(_HERE, "_ref", "libffr_ref_f32.so")  # float/uint32_t configuration
 
 ffr = importlib.import_module("flame-fractal-renderer_b200")
 
 _u64p = C.POINTER(C.c_uint64)
 _f64p = C.POINTER(C.c_double)
 _oracle = None
-_ref = None
+_ref = {}
 
 
-def have_ref():
-    return os.path.exists(REF_LIB)
+def have_ref(elem_size=8):
+    return os.path.exists(REF_LIB if elem_size == 8 else REF_LIB_F32)
 
 
 def oracle():
@@ -54,10 +55,13 @@ def oracle():
     return _oracle
 
 
-def ref():
-    global _ref
-    if _ref is None:
-        l = C.CDLL(REF_LIB)
+def ref(elem_size=8):
+    """The unmodified reference behind ref_harness.cpp: elem_size 8 = as shipped (double /
+    uint64_t), 4 = its float / uint32_t configuration (`make -C oracle ref32`)."""
+    if elem_size not in _ref:
+        l = C.CDLL(REF_LIB if elem_size == 8 else REF_LIB_F32)
+        l.ref_elem_size.restype = C.c_int
+        assert l.ref_elem_size() == elem_size
         l.ref_last_error.restype = C.c_char_p
         l.ref_splitmix64.restype = C.c_uint64
         l.ref_splitmix64.argtypes = [C.c_uint64]
@@ -72,8 +76,8 @@ def ref():
         l.ref_render_mt.argtypes = [C.c_char_p] + [C.c_uint64] * 4 + [
             C.POINTER(C.c_double), C.c_void_p, C.c_uint64, C.POINTER(ffr.FfrStats)]
         l.ref_iterate_points.argtypes = [C.c_char_p, C.c_int64, C.c_uint64, _u64p, _f64p, _f64p]
-        _ref = l
-    return _ref
+        _ref[elem_size] = l
+    return _ref[elem_size]
 
 
 def resize_json(text, size):
@@ -158,45 +162,49 @@ def oracle_isaac_words(seed, n):
     return out
 
 
-def _ref_err(rc):
+def _ref_err(rc, elem_size=8):
     if rc < 0:
-        raise RuntimeError("reference: " + ref().ref_last_error().decode())
+        raise RuntimeError("reference: " + ref(elem_size).ref_last_error().decode())
+
+
+def _dtype(elem_size):
+    return np.uint64 if elem_size == 8 else np.uint32
 
 
 def _enc(text):
     return text.encode() if isinstance(text, str) else text
 
 
-def ref_isaac_words(seed, n):
+def ref_isaac_words(seed, n, elem_size=8):
     out = np.empty(n, dtype=np.uint64)
-    ref().ref_isaac_words(seed, n, out.ctypes.data_as(_u64p))
+    ref(elem_size).ref_isaac_words(seed, n, out.ctypes.data_as(_u64p))
     return out
 
 
-def ref_flame_info(text):
+def ref_flame_info(text, elem_size=8):
     n = C.c_uint64()
     ids = (C.c_uint64 * 256)()
     cw = (C.c_double * 256)()
     md = (C.c_double * 3)()
     mi = (C.c_uint64 * 3)()
     cells, cs = C.c_uint64(), C.c_uint64()
-    _ref_err(ref().ref_flame_info(_enc(text), C.byref(n), ids, cw, md, mi, C.byref(cells),
-                                  C.byref(cs)))
-    dims = ref().ref_json_dims(_enc(text))
+    _ref_err(ref(elem_size).ref_flame_info(_enc(text), C.byref(n), ids, cw, md, mi, C.byref(cells),
+                                           C.byref(cs)), elem_size)
+    dims = ref(elem_size).ref_json_dims(_enc(text))
     k = n.value
     return {"ids": list(ids)[:k], "cw": list(cw)[:k], "mult_d": list(md)[:dims],
             "mult_i": list(mi)[:dims], "cells": cells.value, "cell_size": cs.value, "dims": dims}
 
 
 def ref_render(text, chain_count, chain_len, base_seed=1, chain_first=0, last_len=0,
-               bv_limit=256):
-    info = ref_flame_info(text)
-    buf = np.zeros(info["cells"] * info["cell_size"], dtype=np.uint64)
+               bv_limit=256, elem_size=8):
+    info = ref_flame_info(text, elem_size)
+    buf = np.zeros(info["cells"] * info["cell_size"], dtype=_dtype(elem_size))
     st = ffr.FfrStats()
-    rc = ref().ref_render_chains(_enc(text), base_seed, chain_first, chain_count, chain_len,
-                                 last_len, bv_limit, buf.ctypes.data_as(C.c_void_p), buf.nbytes,
-                                 C.byref(st))
-    _ref_err(rc)
+    rc = ref(elem_size).ref_render_chains(_enc(text), base_seed, chain_first, chain_count, chain_len,
+                                          last_len, bv_limit, buf.ctypes.data_as(C.c_void_p),
+                                          buf.nbytes, C.byref(st))
+    _ref_err(rc, elem_size)
     n_ids = len(json_xforms_count(text))
     return buf, ffr.stats_to_dict(st, info["dims"], n_ids), rc == 0
 
@@ -230,11 +238,11 @@ def ref_render_mt(text, samples, threads, batch, bv_limit=256, want_buffer=False
     return secs.value, ffr.stats_to_dict(st, info["dims"], len(json_xforms_count(text))), buf
 
 
-def ref_iterate_points(text, xf_index, seeds, pts):
+def ref_iterate_points(text, xf_index, seeds, pts, elem_size=8):
     pts = np.ascontiguousarray(pts, dtype=np.float64)
     seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
     out = np.empty_like(pts)
-    _ref_err(ref().ref_iterate_points(_enc(text), xf_index, len(seeds),
-                                      seeds.ctypes.data_as(_u64p), pts.ctypes.data_as(_f64p),
-                                      out.ctypes.data_as(_f64p)))
+    _ref_err(ref(elem_size).ref_iterate_points(_enc(text), xf_index, len(seeds),
+                                               seeds.ctypes.data_as(_u64p), pts.ctypes.data_as(_f64p),
+                                               out.ctypes.data_as(_f64p)), elem_size)
     return out

@@ -59,3 +59,30 @@ def test_reference_threaded_render_runs(ffr, po, examples):
     secs, st, buf = po.ref_render_mt(text, 200_000, 2, 4096, want_buffer=True)
     assert st["s_iter"] == 200_000 and st["s_plot"] == 200_000
     assert int(buf.sum()) == 200_000 and secs > 0
+
+
+@pytest.mark.skipif(not pyoracle.have_ref(4), reason="oracle/_ref/libffr_ref_f32.so not built")
+def test_float_build_flatten_matches_float_reference(ffr, po, examples):
+    """f2 host side: with elem_size 4 the flame model runs every constructor in float like the
+    reference compiled with num_t = float (types.hpp:24-41): xform order, cumulative weights and
+    index multipliers must be the float reference's, value for value."""
+    texts = [examples.example_json(n) for n in examples.EXAMPLES]
+    texts += [flames.variation_flame(v, dims=2, final=True) for v in flames.ALL_VARIATIONS]
+    texts += [flames.many_xforms_flame(), flames.one_d_flame()]
+    for text in texts:
+        f = ffr.Flame(text, elem_size=4)
+        info = po.ref_flame_info(text, elem_size=4)
+        md, mi, cells, cs = f.layout()
+        assert f.elem_size == 4
+        assert f.xform_ids == info["ids"]
+        assert f.cumulative_weights == info["cw"]
+        assert md == info["mult_d"] and mi == info["mult_i"]
+        assert cells == info["cells"] and cs == info["cell_size"]
+        # every stored value is exactly a float
+        for i in range(f.desc.num_xforms):
+            x = f.desc.xforms[i]
+            vals = list(x.pre_A) + list(x.pre_b) + [x.weight, x.color_speed]
+            vals += [x.vars[k].params[q] for k in range(x.num_vars) for q in range(8)]
+            assert all(float(np.float32(v)) == v for v in vals)
+    # ISAAC-32 known answers of the float build
+    assert list(po.ref_isaac_words(1, 4, elem_size=4)) == [676671429, 3101584658, 2918577689, 525991190]
