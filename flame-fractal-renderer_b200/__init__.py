@@ -88,7 +88,20 @@ class FfrStats(C.Structure):
 class FfrOptions(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("scatter_mode", C.c_uint32),
                 ("regroup", C.c_uint32), ("blocks_per_sm", C.c_uint32),
-                ("external_buffer", C.c_void_p), ("stream", C.c_void_p)]
+                ("external_buffer", C.c_void_p), ("stream", C.c_void_p),
+                ("jit", C.c_uint32), ("reserved0", C.c_uint32)]
+
+
+JIT_AUTO, JIT_OFF, JIT_ON = 0, 1, 2
+
+
+class FfrJitInfo(C.Structure):
+    _fields_ = [("active", C.c_uint32), ("eligible", C.c_uint32), ("failed", C.c_uint32),
+                ("from_cache", C.c_uint32), ("threads_per_block", C.c_uint32),
+                ("slots_per_block", C.c_uint32), ("blocks_per_sm", C.c_uint32),
+                ("registers", C.c_uint32), ("smem_bytes", C.c_uint64),
+                ("cubin_bytes", C.c_uint64), ("source_bytes", C.c_uint64),
+                ("compile_seconds", C.c_double), ("message", C.c_char * 256)]
 
 
 class FfrTonemapInfo(C.Structure):
@@ -150,6 +163,11 @@ ABI = {
                                    C.POINTER(FfrTonemapInfo)]),
     "ffr_cuda_iterate_points": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, _u64p, _f64p, _f64p]),
     "ffr_cuda_isaac_words": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, _u64p]),
+    "ffr_cuda_jit_info": (C.c_int, [C.c_void_p, C.POINTER(FfrJitInfo)]),
+    "ffr_cuda_jit_enable": (C.c_int, [C.c_void_p]),
+    "ffr_cuda_jit_source": (C.c_size_t, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "ffr_cuda_jit_compile": (C.c_int, [_descp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                       C.c_char_p, C.c_size_t]),
     "ffr_cuda_atomic_roofline": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
     "ffr_cuda_atomic_roofline_ex": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float),
                                               _u64p]),
@@ -268,14 +286,14 @@ class BufferRenderer:
     """BufferRenderer<dims> on the GPU(s) through the C ABI."""
 
     def __init__(self, flame, devices=None, scatter_mode=SCATTER_AUTO, regroup=0,
-                 blocks_per_sm=0, external_buffer=None, stream=None):
+                 blocks_per_sm=0, external_buffer=None, stream=None, jit=JIT_AUTO):
         self.flame = flame
         L = lib()
         if devices is None:
             devices = [0]
         devs = (C.c_int * len(devices))(*devices)
         opt = FfrOptions(C.sizeof(FfrOptions), scatter_mode, regroup, blocks_per_sm,
-                         external_buffer, stream)
+                         external_buffer, stream, jit, 0)
         err = C.create_string_buffer(512)
         self._h = L.ffr_cuda_create_ex(flame.desc_p, devs, len(devices), C.byref(opt),
                                        err, len(err))
@@ -349,6 +367,25 @@ class BufferRenderer:
     def reduce(self):
         self._check(lib().ffr_cuda_reduce(self._h))
 
+    @property
+    def jit_info(self):
+        """State of the run-time compiled flame-specialised kernel (ffr_jit_info)."""
+        info = FfrJitInfo()
+        self._check(lib().ffr_cuda_jit_info(self._h, C.byref(info)))
+        d = {k: getattr(info, k) for k, _ in FfrJitInfo._fields_}
+        d["message"] = d["message"].decode(errors="replace")
+        return d
+
+    def jit_enable(self):
+        self._check(lib().ffr_cuda_jit_enable(self._h))
+
+    @property
+    def jit_source(self):
+        n = lib().ffr_cuda_jit_source(self._h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib().ffr_cuda_jit_source(self._h, buf, n + 1)
+        return buf.value.decode()
+
     def device_buffer(self, dev_index=0):
         return lib().ffr_cuda_device_buffer(self._h, dev_index)
 
@@ -399,6 +436,18 @@ class BufferRenderer:
         self._check(lib().ffr_cuda_atomic_roofline_ex(self._h, n_atomics, pattern, C.byref(ms),
                                                       C.byref(n)))
         return ms.value, n.value
+
+
+def jit_compile(flame):
+    """Generate and compile the flame-specialised kernel without a device: (source, cubin
+    bytes). Raises FfrError with the NVRTC log on failure."""
+    src = C.create_string_buffer(1 << 20)
+    err = C.create_string_buffer(8192)
+    n = C.c_size_t()
+    rc = lib().ffr_cuda_jit_compile(flame.desc_p, src, len(src), C.byref(n), err, len(err))
+    if rc != FFR_OK:
+        raise FfrError("jit_compile: %s" % err.value.decode(errors="replace"))
+    return src.value.decode(), n.value
 
 
 def split_counts_colors(raw, cells, color_dims):

@@ -13,6 +13,7 @@ point that computes needs an sm_100 device and fails loudly without one.
 #include <vector>
 
 #include "ffr_kernels.cuh"
+#include "ffr_jit_host.cuh"
 
 #define FFR_VERSION_STRING "ffr-b200 0.2 (sm_100a, double/u64 + float/u32)"
 
@@ -137,6 +138,9 @@ struct DeviceState
     int sm_count = 0;
     int blocks_per_sm = 0;
     bool dirty = false;            /* holds samples not yet reduced into device 0 */
+    jit::Module jmod;              /* K1c: the flame-specialised kernel loaded on this device */
+    int jit_blocks_per_sm = 0;
+    void *d_rsl_jit = nullptr;     /* K1c randrsl scratch */
 };
 
 typedef void (*render_fn)(const RenderParams);
@@ -165,6 +169,14 @@ struct ffr_ctx
     u64 launches = 0;
     std::string err;
     bool peer_enabled = false;
+    /* K1c, the run-time compiled flame-specialised kernel (ffr_jit_kernel.cuh) */
+    uint32_t jit_mode = 0;         /* 0 auto (lazy, large renders), 1 off, 2 on at create */
+    bool jit_eligible = false, jit_ready = false, jit_failed = false, jit_cached = false;
+    jit::Config jit_cfg;
+    size_t jit_smem = 0;
+    double jit_compile_s = 0.0;
+    std::string jit_source, jit_err;
+    std::vector<char> jit_cubin;
 };
 
 namespace
@@ -530,6 +542,110 @@ int setup_device(ffr_ctx *ctx, DeviceState &ds, int dev, const ffr_options &opt)
     return FFR_OK;
 }
 
+
+/* ---- K1c: flame-specialised kernel, compiled at run time (ffr_jit_host.cuh) ---- */
+
+int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+/* K1c keeps one slot queue per xform and colour state in registers */
+bool jit_supported(const ffr_ctx *ctx)
+{
+    return ctx->num_xforms >= 1 && ctx->num_xforms <= 8 && ctx->r <= 4;
+}
+
+/* generate the source for this flame and compile it (no device needed) */
+bool jit_prepare(ffr_ctx *ctx)
+{
+    if (!ctx->jit_cubin.empty())
+        return true;
+    jit::Config &cfg = ctx->jit_cfg;
+    cfg.tpb = env_int("FFR_JIT_TPB",256);
+    cfg.minb = env_int("FFR_JIT_MINB",2);
+    cfg.inline_math = env_int("FFR_JIT_INLINE_MATH",0) != 0;
+    /* slots per block: as many as fit next to a second block in the 227 KB of an SM */
+    const size_t per_slot = (size_t)20*ctx->elem + (size_t)(ctx->dims + ctx->r)*ctx->elem + 4u*ctx->num_xforms;
+    int ns = env_int("FFR_JIT_NS",0);
+    if (ns <= 0)
+    {
+        const size_t budget = (227u*1024u)/(size_t)cfg.minb - 2048u;
+        ns = (int)(budget/per_slot);
+        if (ns > 1024) ns = 1024;
+    }
+    ns -= ns % cfg.tpb;
+    if (ns < cfg.tpb || ns > 65535 || cfg.tpb < 64 || cfg.tpb % 32)
+    {
+        ctx->jit_err = "K1c: no valid slot count for this flame";
+        return false;
+    }
+    cfg.ns = ns;
+    ctx->jit_smem = per_slot*(size_t)ns;
+    u64 m0[16];
+    unsigned int m0_32[16];
+    isaac_m0(m0);
+    isaac_m0_32(m0_32);
+    ctx->jit_source = ctx->elem == 8 ? jit::generate<double>(ctx->blob,ctx->colors,m0,m0_32,cfg)
+                                     : jit::generate<float>(ctx->blob,ctx->colors,m0,m0_32,cfg);
+    if (!jit::compile(ctx->jit_source,ctx->jit_cubin,ctx->jit_err,&ctx->jit_compile_s,&ctx->jit_cached))
+    {
+        ctx->jit_cubin.clear();
+        return false;
+    }
+    return true;
+}
+
+/* compile if necessary and load the kernel on every device of the context */
+int jit_activate(ffr_ctx *ctx)
+{
+    if (ctx->jit_ready)
+        return FFR_OK;
+    if (ctx->jit_failed || !ctx->jit_eligible)
+        return FFR_E_UNSUPPORTED;
+    if (!jit_prepare(ctx))
+    {
+        ctx->jit_failed = true;
+        return FFR_E_UNSUPPORTED;
+    }
+    for (DeviceState &ds : ctx->devs)
+    {
+        CK(cudaSetDevice(ds.dev));
+        CK(cudaFree(0));
+        if (!jit::load(ctx->jit_cubin,ctx->jit_smem,ds.jmod,ctx->jit_err))
+        {
+            ctx->jit_failed = true;
+            return FFR_E_UNSUPPORTED;
+        }
+        int nb = 0;
+        jit::Api &a = jit::api(true);
+        if (a.Occupancy(&nb,ds.jmod.fn,ctx->jit_cfg.tpb,ctx->jit_smem) != CUDA_SUCCESS || nb < 1)
+        {
+            ctx->jit_err = "K1c does not fit on the device";
+            ctx->jit_failed = true;
+            return FFR_E_UNSUPPORTED;
+        }
+        if (ctx->opt.blocks_per_sm && (int)ctx->opt.blocks_per_sm < nb)
+            nb = (int)ctx->opt.blocks_per_sm;
+        ds.jit_blocks_per_sm = nb;
+        CK(cudaMalloc(&ds.d_rsl_jit,(size_t)ds.sm_count*nb*16*ctx->jit_cfg.ns*ctx->elem));
+    }
+    ctx->jit_ready = true;
+    return FFR_OK;
+}
+
+/* auto mode: a render this large repays the compile (seconds) many times over */
+void jit_maybe(ffr_ctx *ctx, u64 samples)
+{
+    if (ctx->jit_ready || ctx->jit_failed || !ctx->jit_eligible || ctx->jit_mode != 0)
+        return;
+    const char *e = getenv("FFR_JIT_MIN_SAMPLES");
+    const double min_samples = (e && *e) ? atof(e) : 2e10;
+    if ((double)samples >= min_samples)
+        jit_activate(ctx);
+}
+
 int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_count, u64 chain_len,
         u64 last_len, u64 base_seed, u64 bv_limit)
 {
@@ -557,17 +673,32 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
         ctx->err = "chain length (batch size) must be below 2^31 on the device path";
         return FFR_E_INVALID;
     }
-    const u64 groups = (chain_count + FFR_TPB - 1) / FFR_TPB;
+    const u64 group_chains = ctx->jit_ready ? (u64)ctx->jit_cfg.ns : (u64)FFR_TPB;
+    const u64 groups = (chain_count + group_chains - 1) / group_chains;
     if (groups > 0xfffffff0ULL)
     {
         ctx->err = "too many chains in one launch";
         return FFR_E_INVALID;
     }
-    u64 grid = (u64)ds.sm_count * ds.blocks_per_sm;
+    u64 grid = (u64)ds.sm_count * (ctx->jit_ready ? ds.jit_blocks_per_sm : ds.blocks_per_sm);
     if (grid > groups)
         grid = groups;
     CK(cudaMemsetAsync(ds.d_counter,0,sizeof(unsigned int),ds.stream));
-    ctx->kernel<<<(unsigned)grid,FFR_TPB,ctx->smem_bytes,ds.stream>>>(prm);
+    if (ctx->jit_ready)
+    {
+        prm.rsl_scratch = ds.d_rsl_jit;
+        void *args[] = {&prm};
+        jit::Api &a = jit::api(true);
+        const CUresult r = a.LaunchKernel(ds.jmod.fn,(unsigned)grid,1,1,(unsigned)ctx->jit_cfg.tpb,1,1,
+            (unsigned)ctx->jit_smem,(CUstream)ds.stream,args,nullptr);
+        if (r != CUDA_SUCCESS)
+        {
+            ctx->err = "cuLaunchKernel(ffr_jit_render): " + jit::cu_err(a,r);
+            return FFR_E_CUDA;
+        }
+    }
+    else
+        ctx->kernel<<<(unsigned)grid,FFR_TPB,ctx->smem_bytes,ds.stream>>>(prm);
     CK(cudaGetLastError());
     ++ctx->launches;
     ds.dirty = true;
@@ -727,6 +858,26 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
         if (rc != FFR_OK)
             return fail(ctx->err);
     }
+    /* K1c (run-time compiled). opt.jit: 0 auto = compiled lazily by the first render call of
+       >= FFR_JIT_MIN_SAMPLES samples, for flames the divergence model sends to K1b; 1 never;
+       2 now, for any flame K1c supports. FFR_JIT=0/1 in the environment overrides auto. */
+    ctx->jit_mode = ctx->opt.jit;
+    if (ctx->jit_mode == 0)
+    {
+        const char *e = getenv("FFR_JIT");
+        if (e && *e == '0') ctx->jit_mode = 1;
+        else if (e && *e == '1') ctx->jit_mode = 2;
+    }
+    ctx->jit_eligible = ctx->jit_mode != 1 && jit_supported(ctx) && (ctx->jit_mode == 2 || ctx->regroup);
+    if (ctx->jit_mode == 2 && ctx->opt.jit == 2)
+    {
+        if (!ctx->jit_eligible)
+            return fail("ffr_cuda_create(): the flame-specialised kernel supports <= 8 xforms and <= 4 colour dimensions");
+        if (jit_activate(ctx) != FFR_OK)
+            return fail("ffr_cuda_create(): run-time compilation failed: " + (ctx->jit_err.empty() ? ctx->err : ctx->jit_err));
+    }
+    else if (ctx->jit_mode == 2 && ctx->jit_eligible)
+        jit_activate(ctx);   /* FFR_JIT=1: best effort, the interpreter kernels remain */
     return ctx;
 }
 
@@ -748,6 +899,8 @@ void ffr_cuda_destroy(ffr_ctx *ctx)
         if (ds.d_counter) cudaFree(ds.d_counter);
         if (ds.d_scratch) cudaFree(ds.d_scratch);
         if (ds.d_rsl) cudaFree(ds.d_rsl);
+        if (ds.d_rsl_jit) cudaFree(ds.d_rsl_jit);
+        if (ds.jmod.mod) jit::unload(ds.jmod);
         if (ds.d_stage) cudaFree(ds.d_stage);
         if (ds.own_stream && ds.stream) cudaStreamDestroy(ds.stream);
     }
@@ -870,6 +1023,8 @@ uint64_t ffr_cuda_resident_chains(const ffr_ctx *ctx)
 {
     if (!ctx || ctx->devs.empty())
         return 0;
+    if (ctx->jit_ready)
+        return (uint64_t)ctx->devs[0].sm_count * ctx->devs[0].jit_blocks_per_sm * ctx->jit_cfg.ns;
     return (uint64_t)ctx->devs[0].sm_count * ctx->devs[0].blocks_per_sm * FFR_TPB;
 }
 
@@ -890,6 +1045,7 @@ int ffr_cuda_render_chains(ffr_ctx *ctx, uint64_t chain_first, uint64_t chain_co
         return FFR_E_INVALID;
     }
     const size_t nd = ctx->devs.size();
+    jit_maybe(ctx,chain_count*chain_len);
     for (DeviceState &ds : ctx->devs)
     {
         int rc = reset_bad(ctx,ds);
@@ -941,6 +1097,7 @@ int ffr_cuda_render(ffr_ctx *ctx, uint64_t samples, uint64_t chain_len, uint64_t
         ctx->err = "BufferRenderer::render(): batch size too small";
         return FFR_E_INVALID;
     }
+    jit_maybe(ctx,samples);
     const u64 chains = (samples + chain_len - 1) / chain_len;
     const u64 last = samples - (chains - 1)*chain_len;
     const u64 last_len = (last == chain_len) ? 0 : last;
@@ -1283,6 +1440,79 @@ int ffr_cuda_isaac_words(ffr_ctx *ctx, uint64_t seed, uint64_t n, uint64_t *out)
     CK(cudaMemcpyAsync(out,d_out,n*8,cudaMemcpyDeviceToHost,ds.stream));
     CK(cudaStreamSynchronize(ds.stream));
     cudaFree(d_out);
+    return FFR_OK;
+}
+
+
+int ffr_cuda_jit_info(const ffr_ctx *ctx, ffr_jit_info *info)
+{
+    if (!ctx || !info)
+        return FFR_E_INVALID;
+    memset(info,0,sizeof(*info));
+    info->active = ctx->jit_ready ? 1u : 0u;
+    info->eligible = ctx->jit_eligible ? 1u : 0u;
+    info->failed = ctx->jit_failed ? 1u : 0u;
+    info->from_cache = ctx->jit_cached ? 1u : 0u;
+    info->threads_per_block = (uint32_t)ctx->jit_cfg.tpb;
+    info->slots_per_block = (uint32_t)ctx->jit_cfg.ns;
+    info->blocks_per_sm = ctx->devs.empty() ? 0u : (uint32_t)ctx->devs[0].jit_blocks_per_sm;
+    info->registers = ctx->devs.empty() ? 0u : (uint32_t)ctx->devs[0].jmod.regs;
+    info->smem_bytes = (uint64_t)ctx->jit_smem;
+    info->cubin_bytes = (uint64_t)ctx->jit_cubin.size();
+    info->source_bytes = (uint64_t)ctx->jit_source.size();
+    info->compile_seconds = ctx->jit_compile_s;
+    snprintf(info->message,sizeof(info->message),"%s",ctx->jit_err.c_str());
+    return FFR_OK;
+}
+
+int ffr_cuda_jit_enable(ffr_ctx *ctx)
+{
+    if (!ctx)
+        return FFR_E_INVALID;
+    if (ctx->jit_mode == 1 || !jit_supported(ctx))
+    {
+        ctx->err = "the flame-specialised kernel is disabled or does not support this flame";
+        return FFR_E_UNSUPPORTED;
+    }
+    ctx->jit_eligible = true;
+    const int rc = jit_activate(ctx);
+    if (rc != FFR_OK && ctx->err.empty())
+        ctx->err = ctx->jit_err;
+    return rc;
+}
+
+size_t ffr_cuda_jit_source(const ffr_ctx *ctx, char *buf, size_t buflen)
+{
+    if (!ctx)
+        return 0;
+    if (buf && buflen)
+        snprintf(buf,buflen,"%s",ctx->jit_source.c_str());
+    return ctx->jit_source.size();
+}
+
+int ffr_cuda_jit_compile(const ffr_flame_desc *desc, char *source, size_t source_len,
+        size_t *cubin_bytes, char *err, size_t errlen)
+{
+    ffr_ctx tmp;
+    std::string msg;
+    auto fail = [&](const std::string &m, int rc)
+    {
+        if (err && errlen)
+            snprintf(err,errlen,"%s",m.c_str());
+        return rc;
+    };
+    const bool f32 = desc && desc->elem_size == 4;
+    if (!(f32 ? pack_blob<float>(&tmp,desc,msg) : pack_blob<double>(&tmp,desc,msg)))
+        return fail(msg,FFR_E_INVALID);
+    if (!jit_supported(&tmp))
+        return fail("the flame-specialised kernel supports <= 8 xforms and <= 4 colour dimensions",FFR_E_UNSUPPORTED);
+    const bool ok = jit_prepare(&tmp);
+    if (source && source_len)
+        snprintf(source,source_len,"%s",tmp.jit_source.c_str());
+    if (!ok)
+        return fail(tmp.jit_err,FFR_E_UNSUPPORTED);
+    if (cubin_bytes)
+        *cubin_bytes = tmp.jit_cubin.size();
     return FFR_OK;
 }
 

@@ -1,0 +1,567 @@
+/*
+ffr_jit_host.cuh -- host side of the flame-specialised kernel K1c (ffr_jit_kernel.cuh):
+  1. generate(): turn the packed flame blob (the very bytes the interpreter kernels read) into
+     CUDA source in which every xform is a straight-line function with literal coefficients;
+     literals are hexadecimal floating point, so the generated code holds exactly the values
+     the blob holds;
+  2. compile(): NVRTC -> sm_100a cubin (-fmad=false like the ahead-of-time build), cached in
+     the process and on disk by a hash of source + headers + compiler version;
+  3. Module: load the cubin into a device's primary context and launch it (driver API).
+libnvrtc and libcuda are opened with dlopen so that libffr_cuda.so keeps loading on a machine
+without them (the CPU test box); a missing library only makes the JIT path unavailable, the
+ahead-of-time kernels then serve every flame.
+*/
+
+#pragma once
+
+#include <cuda.h>
+#include <nvrtc.h>
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <sstream>
+
+#include "ffr_params.cuh"
+
+/* the device headers, embedded at build time (Makefile: build/ffr_embed.inc) */
+#include "ffr_embed.inc"
+
+namespace jit
+{
+
+struct Config
+{
+    int tpb = 256;          /* threads per block */
+    int ns = 512;           /* chain slots per block (multiple of tpb) */
+    int minb = 2;           /* blocks per SM asked of ptxas (register cap) */
+    bool inline_math = false;
+};
+
+struct Api
+{
+    bool tried = false, ok = false;
+    std::string err;
+    decltype(&nvrtcCreateProgram) CreateProgram = nullptr;
+    decltype(&nvrtcCompileProgram) CompileProgram = nullptr;
+    decltype(&nvrtcDestroyProgram) DestroyProgram = nullptr;
+    decltype(&nvrtcGetProgramLogSize) GetProgramLogSize = nullptr;
+    decltype(&nvrtcGetProgramLog) GetProgramLog = nullptr;
+    decltype(&nvrtcGetCUBINSize) GetCUBINSize = nullptr;
+    decltype(&nvrtcGetCUBIN) GetCUBIN = nullptr;
+    decltype(&nvrtcVersion) Version = nullptr;
+    decltype(&cuModuleLoadData) ModuleLoadData = nullptr;
+    decltype(&cuModuleUnload) ModuleUnload = nullptr;
+    decltype(&cuModuleGetFunction) ModuleGetFunction = nullptr;
+    decltype(&cuFuncSetAttribute) FuncSetAttribute = nullptr;
+    decltype(&cuFuncGetAttribute) FuncGetAttribute = nullptr;
+    decltype(&cuOccupancyMaxActiveBlocksPerMultiprocessor) Occupancy = nullptr;
+    decltype(&cuLaunchKernel) LaunchKernel = nullptr;
+    decltype(&cuGetErrorString) GetErrorString = nullptr;
+};
+
+inline void *open_first(const char *const *names)
+{
+    for (; *names; ++names)
+        if (void *h = dlopen(*names,RTLD_NOW|RTLD_GLOBAL))
+            return h;
+    return nullptr;
+}
+
+/* need_driver = false: only the compiler (source generation + NVRTC work without a GPU) */
+inline Api &api(bool need_driver)
+{
+    static Api a;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!a.tried)
+    {
+        a.tried = true;
+        static const char *const rtc[] = {"libnvrtc.so.12","libnvrtc.so",
+            "/usr/local/cuda/lib64/libnvrtc.so.12","/usr/local/cuda/lib64/libnvrtc.so",nullptr};
+        void *h = open_first(rtc);
+        if (!h)
+        {
+            a.err = "libnvrtc not found";
+            return a;
+        }
+#define RTC_SYM(field,name) a.field = (decltype(a.field))dlsym(h,#name); if (!a.field) { a.err = "libnvrtc: missing " #name; return a; }
+        RTC_SYM(CreateProgram,nvrtcCreateProgram)
+        RTC_SYM(CompileProgram,nvrtcCompileProgram)
+        RTC_SYM(DestroyProgram,nvrtcDestroyProgram)
+        RTC_SYM(GetProgramLogSize,nvrtcGetProgramLogSize)
+        RTC_SYM(GetProgramLog,nvrtcGetProgramLog)
+        RTC_SYM(GetCUBINSize,nvrtcGetCUBINSize)
+        RTC_SYM(GetCUBIN,nvrtcGetCUBIN)
+        RTC_SYM(Version,nvrtcVersion)
+#undef RTC_SYM
+        a.ok = true;
+    }
+    if (a.ok && need_driver && !a.LaunchKernel)
+    {
+        static const char *const drv[] = {"libcuda.so.1","libcuda.so",nullptr};
+        void *h = open_first(drv);
+        if (!h)
+        {
+            a.err = "libcuda not found";
+            return a;
+        }
+#define DRV_SYM(field,name) a.field = (decltype(a.field))dlsym(h,#name); if (!a.field) { a.err = "libcuda: missing " #name; return a; }
+        DRV_SYM(ModuleLoadData,cuModuleLoadData)
+        DRV_SYM(ModuleUnload,cuModuleUnload)
+        DRV_SYM(ModuleGetFunction,cuModuleGetFunction)
+        DRV_SYM(FuncSetAttribute,cuFuncSetAttribute)
+        DRV_SYM(FuncGetAttribute,cuFuncGetAttribute)
+        DRV_SYM(Occupancy,cuOccupancyMaxActiveBlocksPerMultiprocessor)
+        DRV_SYM(GetErrorString,cuGetErrorString)
+        DRV_SYM(LaunchKernel,cuLaunchKernel)
+#undef DRV_SYM
+    }
+    return a;
+}
+
+/* ---- source generation ---- */
+
+inline std::string lit(double v)
+{
+    char buf[80];
+    if (std::isfinite(v))
+        snprintf(buf,sizeof(buf),"%a",v);
+    else
+    {
+        unsigned long long b;
+        memcpy(&b,&v,8);
+        snprintf(buf,sizeof(buf),"__longlong_as_double((long long)0x%llxULL)",b);
+    }
+    return buf;
+}
+
+inline std::string lit(float v)
+{
+    char buf[80];
+    if (std::isfinite(v))
+        snprintf(buf,sizeof(buf),"%af",(double)v);
+    else
+    {
+        unsigned int b;
+        memcpy(&b,&v,4);
+        snprintf(buf,sizeof(buf),"__uint_as_float(0x%xu)",b);
+    }
+    return buf;
+}
+
+/* Flame constants go to a __constant__ table (jc[]) rather than into the instruction stream:
+   an fp64 literal costs two move instructions at every use, a constant-bank operand none.
+   0 and +-1 stay literals so that the compiler can drop exact no-ops (x*1.0). */
+template <typename T> struct Pool
+{
+    std::vector<T> vals;
+    std::string ref(T v)
+    {
+        if (v == (T)0 || v == (T)1 || v == (T)-1 || !std::isfinite(v))
+            return lit(v);
+        size_t i = 0;
+        for (; i < vals.size(); ++i)
+            if (memcmp(&vals[i],&v,sizeof(T)) == 0)
+                break;
+        if (i == vals.size())
+            vals.push_back(v);
+        return "jc[" + std::to_string(i) + "]";
+    }
+};
+
+template <typename T>
+void emit_affine(std::ostringstream &o, Pool<T> &pool, int D, const T *A, const T *b, const char *in, const char *out)
+{
+    o << "    { const T A[" << D*D << "] = {";
+    for (int i = 0; i < D*D; ++i)
+        o << (i ? "," : "") << pool.ref(A[i]);
+    o << "}; const T b[" << D << "] = {";
+    for (int i = 0; i < D; ++i)
+        o << (i ? "," : "") << pool.ref(b[i]);
+    o << "}; affine_apply<T,JD>(A,b," << in << "," << out << "); }\n";
+}
+
+/* XForm::applyIteration (types/xform.hpp:211-227) for ONE xform, unrolled: the same statements
+   xform_apply_fn (ffr_device.cuh) executes for this xform, in the same order */
+template <typename T>
+void emit_xform(std::ostringstream &o, Pool<T> &pool, const std::string &name, int D, const DevXFormT<T> &xf,
+        const DevVarT<T> *vars)
+{
+    o << "__device__ __forceinline__ void " << name << "(const JT *pin, JT *pout, RngT<JT> &rng)\n{\n";
+    o << "    typedef JT T;\n    T t[JD], v[JD];\n";
+    if (D < 3 || (xf.flags & XF_HAS_PRE))
+        emit_affine<T>(o,pool,D,xf.pre_A,xf.pre_b,"pin","t");
+    else
+        o << "    for (int i = 0; i < JD; ++i) t[i] = pin[i];\n";
+    o << "    for (int i = 0; i < JD; ++i) v[i] = 0.0;\n";
+    o << "    PolarT<T> P; P.r2 = P.r = P.ang = P.sa = P.ca = 0.0;\n";
+    if (D == 2)
+        o << "    polar_fill(P," << xf.need << "u,t[0],t[1]);\n";
+    for (uint32_t k = xf.var_begin; k < xf.var_begin + xf.var_count; ++k)
+    {
+        const DevVarT<T> &var = vars[k];
+        o << "    {\n        DevVarT<T> var; var.op = " << var.op << "u; var.axis_x = " << var.axis_x
+          << "u; var.axis_y = " << var.axis_y << "u; var.need = " << var.need << "u; var.weight = "
+          << pool.ref(var.weight) << ";\n       ";
+        for (int q = 0; q < FFR_MAX_VAR_PARAMS; ++q)
+            o << " var.p[" << q << "] = " << pool.ref(var.p[q]) << ";";
+        o << "\n        T c[JD];\n";
+        const bool v2d = D >= 2 && var.op >= FFR_VAR_FIRST_2D && var.op <= FFR_VAR_LAST_2D;
+        if (var.op == FFR_VAR_LINEAR)
+            o << "        for (int i = 0; i < JD; ++i) c[i] = t[i];\n";
+        else if (v2d)
+        {
+            if (D > 2)
+            {
+                /* VariationFrom2D::calc_h, variations.hpp:94-105 */
+                o << "        const T a0 = t[" << var.axis_x << "], a1 = t[" << var.axis_y << "];\n";
+                o << "        polar_fill(P," << var.need << "u,a0,a1);\n";
+            }
+            else
+                o << "        const T a0 = t[0], a1 = t[1];\n";
+            o << "        T ox, oy;\n        calc2d_body<T," << var.op << "u>(var,rng,P,a0,a1,ox,oy);\n";
+            if (D > 2)
+            {
+                for (int i = 0; i < D; ++i)
+                    o << "        c[" << i << "] = " << ((uint32_t)i == var.axis_x ? "ox" :
+                        ((uint32_t)i == var.axis_y ? "oy" : "0.0")) << ";\n";
+            }
+            else
+                o << "        c[0] = ox; c[1] = oy;\n";
+        }
+        else
+        {
+            o << "        for (int i = 0; i < JD; ++i) c[i] = 0.0;\n";
+            o << "        calc_nd_body<T,JD," << var.op << "u>(var,rng,t,c);\n";
+        }
+        /* v += weight * calc(t): calc[i]*weight then add (point.hpp:215-225) */
+        o << "        for (int i = 0; i < JD; ++i) v[i] += c[i] * var.weight;\n    }\n";
+    }
+    if (D < 3 || (xf.flags & XF_HAS_POST))
+        emit_affine<T>(o,pool,D,xf.post_A,xf.post_b,"v","pout");
+    else
+        o << "    for (int i = 0; i < JD; ++i) pout[i] = v[i];\n";
+    o << "}\n\n";
+}
+
+template <typename T>
+void emit_blend(std::ostringstream &o, Pool<T> &pool, int R, const DevXFormT<T> &xf, const T *colors,
+        const char *src, const char *dst, const char *indent)
+{
+    /* (1.0 - s)*c + s*colour with s and colour of type num_t (render_iterator.hpp:118-121,128-131) */
+    o << indent << "{ const T s = " << pool.ref(xf.color_speed) << ";";
+    for (int j = 0; j < R; ++j)
+        o << " { const T col = " << pool.ref(colors[xf.color_off + j]) << "; " << dst << "[" << j
+          << "] = (1.0-s)*" << src << "[" << j << "] + s*col; }";
+    o << " }\n";
+}
+
+template <typename T>
+std::string generate(const std::vector<unsigned char> &blobv, const std::vector<unsigned char> &colorsv,
+        const u64 *m0, const unsigned int *m0_32, const Config &cfg)
+{
+    const unsigned char *blob = blobv.data();
+    const DevFlameT<T> *fl = (const DevFlameT<T>*)blob;
+    const DevXFormT<T> *xfs = (const DevXFormT<T>*)(blob + fl->xf_off);
+    const DevVarT<T> *vars = (const DevVarT<T>*)(blob + fl->var_off);
+    const T *colors = (const T*)colorsv.data();
+    const int D = (int)fl->dims, R = (int)fl->r, NX = (int)fl->num_xforms;
+    std::ostringstream h, o;   /* head (needs the finished constant pool) and body */
+    Pool<T> pool;
+    h << "/* generated by libffr_cuda for one flame: K1c, see ffr_jit_kernel.cuh */\n";
+    h << "#define FFR_TPB " << cfg.ns << "\n";
+    if (cfg.inline_math)
+        h << "#define FFR_MATH_ATTR __forceinline__\n";
+    h << "#define FFR_ISAAC_M0_INIT {";
+    for (int i = 0; i < 16; ++i)
+        h << (i ? "," : "") << m0[i] << "ULL";
+    h << "}\n#define FFR_ISAAC_M0_32_INIT {";
+    for (int i = 0; i < 16; ++i)
+        h << (i ? "," : "") << m0_32[i] << "u";
+    h << "}\n";
+    h << "#include \"ffr_params.cuh\"\n";
+    h << "typedef " << (sizeof(T) == 8 ? "double" : "float") << " JT;\n";
+    h << "#define JD " << D << "\n#define JR " << R << "\n#define JNX " << NX << "\n#define JNS " << cfg.ns
+      << "\n#define JTPB " << cfg.tpb << "\n#define JMINB " << cfg.minb << "\n#define JHAS_FINAL "
+      << (fl->has_final ? 1 : 0) << "\n#define JANY_RNG " << (fl->uses_rng ? 1 : 0) << "\n\n";
+    for (int k = 0; k < NX + (fl->has_final ? 1 : 0); ++k)
+        emit_xform<T>(o,pool,"jx_" + std::to_string(k),D,xfs[k],vars);
+    /* xform dispatch (the index is warp-uniform in K1c's hot loop) */
+    o << "__device__ __forceinline__ void jit_xform(unsigned k, const JT *pin, JT *pout, RngT<JT> &rng)\n{\n    switch (k)\n    {\n";
+    for (int k = 0; k < NX; ++k)
+    {
+        if (k + 1 < NX) o << "    case " << k << ":";
+        else o << "    default:";
+        o << " jx_" << k << "(pin,pout,rng); break;\n";
+    }
+    o << "    }\n}\n\n";
+    o << "__device__ __forceinline__ void jit_final(const JT *pin, JT *pout, RngT<JT> &rng)\n{\n";
+    if (fl->has_final)
+        o << "    jx_" << NX << "(pin,pout,rng);\n";
+    else
+        o << "    for (int i = 0; i < JD; ++i) pout[i] = pin[i];\n";
+    o << "}\n\n";
+    /* Flame::getRandomXForm (types/flame.hpp:212-219): number of table entries below r */
+    o << "__device__ __forceinline__ unsigned jit_select(JT r)\n{\n    unsigned i = 0;\n";
+    for (int k = 0; k + 1 < NX; ++k)
+        o << "    i += (" << pool.ref(fl->xfcw[k]) << " < r) ? 1u : 0u;\n";
+    o << "    return i;\n}\n\n";
+    o << "__device__ __forceinline__ bool jit_inb(const JT *pf)\n{\n    bool inb = true;\n";
+    for (int i = 0; i < D; ++i)
+        o << "    inb &= (pf[" << i << "] >= " << pool.ref(fl->lo[i]) << ") && (pf[" << i << "] <= " << pool.ref(fl->hi[i]) << ");\n";
+    o << "    return inb;\n}\n\n";
+    /* buffer_renderer.hpp:202-209 */
+    o << "__device__ __forceinline__ u64 jit_index(const JT *pf)\n{\n";
+    o << "    u64 bi = to_index((pf[0] - " << pool.ref(fl->lo[0]) << ") * " << pool.ref(fl->mult_d[0]) << ");\n";
+    for (int i = 1; i < D; ++i)
+        o << "    bi += to_index((pf[" << i << "] - " << pool.ref(fl->lo[i]) << ") * " << pool.ref(fl->mult_d[i]) << ") * "
+          << fl->mult_i[i] << "ULL;\n";
+    o << "    return bi;\n}\n\n";
+    o << "__device__ __forceinline__ void jit_color(unsigned k, JT *c)\n{\n    typedef JT T;\n    switch (k)\n    {\n";
+    for (int k = 0; k < NX; ++k)
+        if (R > 0 && (xfs[k].flags & XF_HAS_COLOR))
+        {
+            o << "    case " << k << ":\n";
+            emit_blend<T>(o,pool,R,xfs[k],colors,"c","c","        ");
+            o << "        break;\n";
+        }
+    o << "    default: break;\n    }\n}\n\n";
+    o << "__device__ __forceinline__ void jit_final_color(const JT *c, JT *cf)\n{\n    typedef JT T;\n";
+    if (R > 0 && fl->has_final && (xfs[NX].flags & XF_HAS_COLOR))
+        emit_blend<T>(o,pool,R,xfs[NX],colors,"c","cf","    ");
+    else
+        o << "    for (int i = 0; i < JR; ++i) cf[i] = c[i];\n";
+    o << "}\n\n";
+    o << "__device__ __forceinline__ u64 jit_json_id(unsigned k)\n{\n    switch (k)\n    {\n";
+    for (int k = 0; k < NX; ++k)
+        o << "    case " << k << ": return " << xfs[k].json_id << "ULL;\n";
+    o << "    default: return 0;\n    }\n}\n\n";
+    o << "#include \"ffr_jit_kernel.cuh\"\n";
+    h << "__constant__ JT jc[" << (pool.vals.empty() ? 1 : pool.vals.size()) << "] = {";
+    for (size_t i = 0; i < pool.vals.size(); ++i)
+        h << (i ? "," : "") << lit(pool.vals[i]);
+    if (pool.vals.empty())
+        h << "0";
+    h << "};\n\n";
+    return h.str() + o.str();
+}
+
+/* ---- compile + cache ---- */
+
+inline u64 fnv1a(const void *data, size_t n, u64 h = 0xcbf29ce484222325ULL)
+{
+    const unsigned char *p = (const unsigned char*)data;
+    for (size_t i = 0; i < n; ++i)
+    {
+        h ^= p[i];
+        h *= 0x100000001b3ULL;
+    }
+    return h;
+}
+
+inline std::string cache_dir()
+{
+    const char *e = getenv("FFR_JIT_CACHE");
+    if (e && *e)
+        return e;
+    return "/tmp/ffr-b200-jit-" + std::to_string((unsigned)getuid());
+}
+
+struct Shim { const char *name; const char *text; size_t len; };
+
+inline const std::vector<Shim> &headers()
+{
+    /* NVRTC has no host headers: the few names the device code takes from them */
+    static const char shim_int[] =
+        "#pragma once\n"
+        "typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t;\n"
+        "typedef unsigned short uint16_t; typedef int int32_t; typedef unsigned int uint32_t;\n"
+        "typedef long long int64_t; typedef unsigned long long uint64_t;\n";
+    static const char shim_math[] =
+        "#pragma once\n"
+        "#define M_PI 3.14159265358979323846\n"
+        "#define M_1_PI 0.31830988618379067154\n"
+        "#define M_PI_4 0.78539816339744830962\n"
+        "#define INFINITY __int_as_float(0x7f800000)\n";
+    static const char shim_empty[] = "#pragma once\n";
+    static const std::vector<Shim> h = {
+        {"ffr_device.cuh",(const char*)ffr_embed_device,ffr_embed_device_len},
+        {"ffr_params.cuh",(const char*)ffr_embed_params,ffr_embed_params_len},
+        {"ffr_jit_kernel.cuh",(const char*)ffr_embed_jit_kernel,ffr_embed_jit_kernel_len},
+        {"../../include/ffr_cuda.h",(const char*)ffr_embed_abi,ffr_embed_abi_len},
+        {"cstdint",shim_int,sizeof(shim_int)-1},
+        {"stdint.h",shim_int,sizeof(shim_int)-1},
+        {"stddef.h",shim_empty,sizeof(shim_empty)-1},
+        {"math.h",shim_math,sizeof(shim_math)-1},
+    };
+    return h;
+}
+
+/* source -> sm_100a cubin. Needs no GPU. */
+inline bool compile(const std::string &src, std::vector<char> &cubin, std::string &err, double *seconds,
+        bool *from_cache)
+{
+    static std::map<u64,std::vector<char>> mem_cache;
+    static std::mutex mu;
+    Api &a = api(false);
+    if (seconds) *seconds = 0.0;
+    if (from_cache) *from_cache = false;
+    if (!a.ok)
+    {
+        err = a.err;
+        return false;
+    }
+    int vmaj = 0, vmin = 0;
+    a.Version(&vmaj,&vmin);
+    u64 h = fnv1a(src.data(),src.size());
+    for (const Shim &s : headers())
+        h = fnv1a(s.text,s.len,h);
+    const int ver[2] = {vmaj,vmin};
+    h = fnv1a(ver,sizeof(ver),h);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = mem_cache.find(h);
+        if (it != mem_cache.end())
+        {
+            cubin = it->second;
+            if (from_cache) *from_cache = true;
+            return true;
+        }
+    }
+    char name[64];
+    snprintf(name,sizeof(name),"/%016llx.cubin",(unsigned long long)h);
+    const std::string dir = cache_dir();
+    const std::string path = dir + name;
+    const char *nocache = getenv("FFR_JIT_NO_DISK_CACHE");
+    if (!(nocache && *nocache == '1'))
+    {
+        if (FILE *f = fopen(path.c_str(),"rb"))
+        {
+            fseek(f,0,SEEK_END);
+            long n = ftell(f);
+            fseek(f,0,SEEK_SET);
+            cubin.resize(n > 0 ? (size_t)n : 0);
+            const bool ok = n > 0 && fread(cubin.data(),1,(size_t)n,f) == (size_t)n;
+            fclose(f);
+            if (ok)
+            {
+                std::lock_guard<std::mutex> lock(mu);
+                mem_cache[h] = cubin;
+                if (from_cache) *from_cache = true;
+                return true;
+            }
+        }
+    }
+    std::vector<const char*> hn, ht;
+    std::vector<std::string> texts;
+    for (const Shim &s : headers())
+        texts.emplace_back(s.text,s.len);     /* NUL-terminated copies */
+    for (size_t i = 0; i < texts.size(); ++i)
+    {
+        hn.push_back(headers()[i].name);
+        ht.push_back(texts[i].c_str());
+    }
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC,&t0);
+    nvrtcProgram prog = nullptr;
+    if (a.CreateProgram(&prog,src.c_str(),"ffr_flame.cu",(int)hn.size(),ht.data(),hn.data()) != NVRTC_SUCCESS)
+    {
+        err = "nvrtcCreateProgram failed";
+        return false;
+    }
+    const char *opts[] = {"--gpu-architecture=sm_100a","-fmad=false","-std=c++17","-lineinfo","-default-device"};
+    const nvrtcResult rc = a.CompileProgram(prog,5,opts);
+    if (rc != NVRTC_SUCCESS)
+    {
+        size_t n = 0;
+        a.GetProgramLogSize(prog,&n);
+        std::string log(n,'\0');
+        if (n) a.GetProgramLog(prog,&log[0]);
+        err = "NVRTC: " + log.substr(0,4000);
+        a.DestroyProgram(&prog);
+        return false;
+    }
+    size_t n = 0;
+    a.GetCUBINSize(prog,&n);
+    cubin.resize(n);
+    a.GetCUBIN(prog,cubin.data());
+    a.DestroyProgram(&prog);
+    clock_gettime(CLOCK_MONOTONIC,&t1);
+    if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9*(double)(t1.tv_nsec - t0.tv_nsec);
+    if (!(nocache && *nocache == '1'))
+    {
+        mkdir(dir.c_str(),0700);
+        const std::string tmp = path + "." + std::to_string((long)getpid());
+        if (FILE *f = fopen(tmp.c_str(),"wb"))
+        {
+            const bool ok = fwrite(cubin.data(),1,cubin.size(),f) == cubin.size();
+            fclose(f);
+            if (!ok || rename(tmp.c_str(),path.c_str()) != 0)
+                unlink(tmp.c_str());
+        }
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    mem_cache[h] = cubin;
+    return true;
+}
+
+/* a cubin loaded into one device's primary context (which must be current) */
+struct Module
+{
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    int regs = 0;
+};
+
+inline std::string cu_err(Api &a, CUresult r)
+{
+    const char *s = nullptr;
+    if (a.GetErrorString) a.GetErrorString(r,&s);
+    return s ? s : "unknown driver error";
+}
+
+inline bool load(const std::vector<char> &cubin, size_t smem, Module &m, std::string &err)
+{
+    Api &a = api(true);
+    if (!a.LaunchKernel)
+    {
+        err = a.err;
+        return false;
+    }
+    CUresult r = a.ModuleLoadData(&m.mod,cubin.data());
+    if (r != CUDA_SUCCESS)
+    {
+        err = "cuModuleLoadData: " + cu_err(a,r);
+        return false;
+    }
+    r = a.ModuleGetFunction(&m.fn,m.mod,"ffr_jit_render");
+    if (r != CUDA_SUCCESS)
+    {
+        err = "cuModuleGetFunction: " + cu_err(a,r);
+        return false;
+    }
+    r = a.FuncSetAttribute(m.fn,CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,(int)smem);
+    if (r != CUDA_SUCCESS)
+    {
+        err = "cuFuncSetAttribute(smem): " + cu_err(a,r);
+        return false;
+    }
+    a.FuncGetAttribute(&m.regs,CU_FUNC_ATTRIBUTE_NUM_REGS,m.fn);
+    return true;
+}
+
+inline void unload(Module &m)
+{
+    Api &a = api(true);
+    if (m.mod && a.ModuleUnload)
+        a.ModuleUnload(m.mod);
+    m.mod = nullptr;
+    m.fn = nullptr;
+}
+
+} // namespace jit

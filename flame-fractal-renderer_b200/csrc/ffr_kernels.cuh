@@ -19,31 +19,7 @@ the result does not depend on which block, SM or GPU runs it.
 #pragma once
 
 #include "ffr_device.cuh"
-
-struct DevStats
-{
-    u64 s_iter, s_plot;
-    u64 xf_dist[FFR_MAX_XFORMS];       /* by SORTED xform index; host maps to JSON ids */
-    u64 pt_min[3], pt_max[3];          /* f64_to_ordered() keys */
-    u64 n_bad;
-    uint32_t abort, pad;
-    u64 bad_xf[FFR_MAX_BAD_RECORDED];  /* JSON ids */
-    double bad_pt[FFR_MAX_BAD_RECORDED][3];
-};
-
-struct RenderParams
-{
-    const void *blob;              /* DevFlameT<T> | DevXFormT<T>[] | DevVarT<T>[] */
-    const void *colors;            /* T[] */
-    void *buffer;                  /* cells x (1+r) elements of sizeof(T) bytes */
-    DevStats *stats;
-    unsigned int *work_counter;
-    void *rsl_scratch;             /* K1b: randrsl columns, 16*FFR_TPB words per block */
-    u64 *trace;                    /* FFR_SCATTER_TRACE: cell index of sample `it` of chain k at
-                                      trace[it*chain_count + k], ~0 when not plotted */
-    u64 chain_first, chain_count, chain_len, last_len, base_seed, bv_limit;
-    uint32_t blob_bytes, scatter_mode;
-};
+#include "ffr_params.cuh"
 
 #define FFR_SMEM_RNG_BYTES_W(WB) (FFR_RNG_WORDS*FFR_TPB*(WB))
 #define FFR_SMEM_RNG_BYTES FFR_SMEM_RNG_BYTES_W(8)
@@ -59,13 +35,6 @@ __device__ __forceinline__ void stage_blob(void *dst, const void *src, uint32_t 
         d[i] = s[i];
     __syncthreads();
 }
-
-/* (size_t)((pf - lo) * mult_d): truncating conversion, buffer_renderer.hpp:202 */
-__device__ __forceinline__ u64 to_index(double v) { return __double2ull_rz(v); }
-__device__ __forceinline__ u64 to_index(float v) { return __float2ull_rz(v); }
-/* ++hist (buffer_renderer.hpp:211-215) for u64 / u32 counters */
-__device__ __forceinline__ void hist_add(u64 *cell, unsigned n) { atomicAdd(cell,(u64)n); }
-__device__ __forceinline__ void hist_add(unsigned int *cell, unsigned n) { atomicAdd(cell,n); }
 
 /* add the 16-bit per-xform selection counters packed in pk0/pk1 to the block's counters */
 __device__ __forceinline__ void flush_packed(unsigned long long *s_xf, u64 &pk0, u64 &pk1)

@@ -248,6 +248,10 @@ typedef struct ffr_options
     void *external_buffer;      /* device pointer (ndev must be 1): render into caller-owned
                                    memory (e.g. a torch tensor) instead of allocating */
     void *stream;               /* cudaStream_t to launch on (ndev must be 1); NULL = own stream */
+    uint32_t jit;               /* flame-specialised kernel compiled at run time (NVRTC): 0 auto (lazily,
+                                   by the first render call large enough to repay the compile), 1 never,
+                                   2 at create (fails if unavailable) */
+    uint32_t reserved0;
 } ffr_options;
 
 typedef struct ffr_ctx ffr_ctx;
@@ -317,6 +321,30 @@ int ffr_cuda_get_stats(ffr_ctx *ctx, ffr_stats *stats);
 uint64_t ffr_cuda_resident_chains(const ffr_ctx *ctx);
 /* number of kernel launches issued by this context so far */
 uint64_t ffr_cuda_launch_count(const ffr_ctx *ctx);
+
+/* ---- the flame-specialised render kernel (run-time compiled; csrc/ffr_jit_kernel.cuh) ----
+   The reference dispatches every variation through a virtual call (variations.hpp:38-59,
+   xform.hpp:218-221); the ahead-of-time kernels interpret a flattened op list; this path turns
+   the flame into straight-line sm_100a code with NVRTC. Results are identical to the
+   interpreter kernels bit for bit (same device functions, same order, -fmad=false). */
+typedef struct ffr_jit_info
+{
+    uint32_t active;            /* renders of this context run the compiled kernel */
+    uint32_t eligible, failed, from_cache;
+    uint32_t threads_per_block, slots_per_block, blocks_per_sm, registers;
+    uint64_t smem_bytes, cubin_bytes, source_bytes;
+    double compile_seconds;     /* NVRTC time of this context's compile (0 when cached) */
+    char message[256];          /* why it is unavailable, if it is */
+} ffr_jit_info;
+int ffr_cuda_jit_info(const ffr_ctx *ctx, ffr_jit_info *info);
+/* compile + load now (what ffr_options.jit = 2 does at create) */
+int ffr_cuda_jit_enable(ffr_ctx *ctx);
+/* the generated CUDA source (empty until compiled); returns its length */
+size_t ffr_cuda_jit_source(const ffr_ctx *ctx, char *buf, size_t buflen);
+/* Generate and compile for a flame WITHOUT a device (NVRTC needs none): the build check of
+   the run-time path. source may be NULL. */
+int ffr_cuda_jit_compile(const ffr_flame_desc *desc, char *source, size_t source_len,
+        size_t *cubin_bytes, char *err, size_t errlen);
 
 /* Sum the per-device private buffers into device 0's buffer over NVLink peer memory
    (no-op for one device). ffr_cuda_read_buffer calls it when needed. */

@@ -235,3 +235,38 @@ def many_xforms_flame(k=20):
                                          0.6 * ((i * 5) % 13) / 13.0 - 0.3]}})
     fl = {"dimensions": 2, "size": [200, 150], "bounds": [[-1, 1], [-1, 1]], "xforms": xfs}
     return json.dumps(fl, indent=1)
+
+
+def multi_variation_flame(names, dims=2, size=None, color=True, final_name=None):
+    """One xform per entry of `names` (<= 7), each running that variation next to a damped
+    linear term, plus a contracting linear xform: many variations per compiled kernel for
+    the run-time compiled path (tests/test_gpu_jit.py)."""
+    if size is None:
+        size = {1: [4096], 2: [128, 128], 3: [32, 32, 32]}[dims]
+    xfs = [{"weight": 1.0,
+            "variations": [variation_entry("linear", 1.0, dims)],
+            "pre_affine": _affine(dims, 0.5, 0.1, [0.3, -0.2, 0.1])}]
+    for i, name in enumerate(names):
+        xfs.append({"weight": 0.5 + 0.1 * i,
+                    "variations": [variation_entry(name, 0.6, dims, ((i + 2) % 3, i % 3) if dims > 2 else (0, 1)),
+                                   variation_entry("linear", 0.25, dims)],
+                    "pre_affine": _affine(dims, 0.8, -0.3 + 0.05 * i, [-0.2, 0.4, 0.3]),
+                    "post_affine": _affine(dims, 0.7, 0.1, [0.1, 0.1 - 0.02 * i, -0.1])})
+    fl = {"dimensions": dims, "size": size, "bounds": [[-3, 3]] * dims, "xforms": xfs}
+    if color:
+        fl["color_dimensions"] = 2
+        fl["color_speed"] = 0.4
+        for i, xf in enumerate(xfs):
+            if i % 2 == 0:
+                xf["color"] = [i / 8.0, 1.0 - i / 8.0]
+        xfs[1]["color_speed"] = 0.8
+    if final_name is not None:
+        fl["final_xform"] = {
+            "variations": [variation_entry("linear", 0.9, dims),
+                           variation_entry(final_name, 0.1, dims, (0, 2))],
+            "post_affine": _affine(dims, 0.9, 0.05, [0.0, 0.1, 0.0]),
+        }
+        if color:
+            fl["final_xform"]["color"] = [0.5, 0.5]
+            fl["final_xform"]["color_speed"] = 0.25
+    return json.dumps(fl, indent=1)

@@ -23,11 +23,14 @@ def main():
     modes = [int(m) for m in os.environ.get("MODES", "1").split(",")]
     bps = int(os.environ.get("BPS", "0"))
     regs = [int(m) for m in os.environ.get("REGROUP", "0").split(",")]
+    jits = [int(m) for m in os.environ.get("JIT", "1").split(",")]   # 1 off, 2 on
     for nm in names:
         ename, size = CONFIGS[nm]
         fl = ffr.Flame(ex.example_json(ename, size=size))
-        for mode, rg in [(m, g) for m in modes for g in regs]:
-            r = ffr.BufferRenderer(fl, scatter_mode=mode, blocks_per_sm=bps, regroup=rg)
+        for mode, rg, jit in [(m, g, j) for m in modes for g in regs for j in jits]:
+            t0 = time.time()
+            r = ffr.BufferRenderer(fl, scatter_mode=mode, blocks_per_sm=bps, regroup=rg, jit=jit)
+            tc = time.time() - t0
             chains = r.resident_chains * waves
             r.render_chains(0, 148 * 2 * 256, 256)  # warm-up
             t0 = time.time()
@@ -35,8 +38,11 @@ def main():
             dt = time.time() - t0
             st = r.stats
             n = chains * L
-            print("%-10s mode %d rg %d  %.3e samples in %.3fs = %.3e samples/s  plotted %.3f" % (
-                nm, mode, rg, n, dt, n / dt, st["s_plot"] / st["s_iter"]), flush=True)
+            ji = r.jit_info
+            print("%-10s mode %d rg %d jit %d  %.3e samples in %.3fs = %.3e samples/s  plotted %.3f  "
+                  "[create %.2fs regs %d slots %d bps %d]" % (
+                nm, mode, rg, jit, n, dt, n / dt, st["s_plot"] / st["s_iter"], tc, ji["registers"],
+                ji["slots_per_block"], ji["blocks_per_sm"]), flush=True)
             r.close()
 
 if __name__ == "__main__":
