@@ -563,20 +563,39 @@ bool jit_prepare(ffr_ctx *ctx)
     if (!ctx->jit_cubin.empty())
         return true;
     jit::Config &cfg = ctx->jit_cfg;
-    cfg.tpb = env_int("FFR_JIT_TPB",256);
+    cfg.async = env_int("FFR_JIT_ASYNC",1) != 0;
+    cfg.tpb = env_int("FFR_JIT_TPB",cfg.async ? 320 : 256);
     cfg.minb = env_int("FFR_JIT_MINB",2);
     cfg.inline_math = env_int("FFR_JIT_INLINE_MATH",0) != 0;
-    /* slots per block: as many as fit next to a second block in the 227 KB of an SM */
-    const size_t per_slot = (size_t)20*ctx->elem + (size_t)(ctx->dims + ctx->r)*ctx->elem + 4u*ctx->num_xforms;
+    /* slots per block: as many as fit next to a second block in the 227 KB of an SM.
+       Per slot: ISAAC randmem[16] + randa/b/c/cnt, the point, the colour, then K1d: 16 packed
+       selections, iteration and chain numbers + one ring entry per queue; K1c: two queue entries per xform */
+    const size_t per_slot = (size_t)20*ctx->elem + (size_t)(ctx->dims + ctx->r)*ctx->elem +
+        (cfg.async ? 16u + 2u*(ctx->num_xforms + 1u) : 4u*ctx->num_xforms);
     int ns = env_int("FFR_JIT_NS",0);
     if (ns <= 0)
     {
         const size_t budget = (227u*1024u)/(size_t)cfg.minb - 2048u;
         ns = (int)(budget/per_slot);
         if (ns > 1024) ns = 1024;
+        if (!cfg.async)
+            ns -= ns % cfg.tpb;
     }
-    ns -= ns % cfg.tpb;
-    if (ns < cfg.tpb || ns > 65535 || cfg.tpb < 64 || cfg.tpb % 32)
+    if (cfg.async)
+    {
+        int p2 = 64;
+        while (p2*2 <= ns) p2 *= 2;
+        ns = p2;             /* ring index = position & (ns-1) */
+        if (!getenv("FFR_JIT_TPB"))
+        {
+            /* keep >= 32 slots per queue out of flight so that full chunks can always be popped */
+            int t = ns - 32*((int)ctx->num_xforms + 1);
+            t -= t % 32;
+            cfg.tpb = std::max(128,std::min(cfg.tpb,t));
+        }
+    }
+    ns -= ns % 32;       /* whole warps seed the slots */
+    if (ns < 64 || ns > 32768 || cfg.tpb < 64 || cfg.tpb % 32 || cfg.tpb > 1024)
     {
         ctx->jit_err = "K1c: no valid slot count for this flame";
         return false;
@@ -673,6 +692,15 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
         ctx->err = "chain length (batch size) must be below 2^31 on the device path";
         return FFR_E_INVALID;
     }
+    if (ctx->jit_ready && ctx->jit_cfg.async && chain_count > (1ULL << 30))
+    {
+        /* K1d hands out chains through a 32-bit counter: split very long launches */
+        const u64 half = 1ULL << 30;
+        int rc = launch_render(ctx,ds,chain_first,half,chain_len,0,base_seed,bv_limit);
+        if (rc != FFR_OK)
+            return rc;
+        return launch_render(ctx,ds,chain_first + half,chain_count - half,chain_len,last_len,base_seed,bv_limit);
+    }
     const u64 group_chains = ctx->jit_ready ? (u64)ctx->jit_cfg.ns : (u64)FFR_TPB;
     const u64 groups = (chain_count + group_chains - 1) / group_chains;
     if (groups > 0xfffffff0ULL)
@@ -728,6 +756,11 @@ int collect_stats(ffr_ctx *ctx, ffr_stats *out)
         CK(cudaMemcpyAsync(&hs[0],ds.d_stats,sizeof(DevStats),cudaMemcpyDeviceToHost,ds.stream));
         CK(cudaStreamSynchronize(ds.stream));
         const DevStats &s = hs[0];
+        if (s.abort & 0x100u)
+        {
+            ctx->err = "render kernel: slot queue watchdog tripped (internal error)";
+            return FFR_E_CUDA;
+        }
         out->s_iter += s.s_iter;
         out->s_plot += s.s_plot;
         for (uint32_t i = 0; i < ctx->num_xforms; ++i)

@@ -40,6 +40,7 @@ struct Config
     int ns = 512;           /* chain slots per block (multiple of tpb) */
     int minb = 2;           /* blocks per SM asked of ptxas (register cap) */
     bool inline_math = false;
+    bool async = true;      /* K1d (ffr_jit_async.cuh, queue scheduled) instead of K1c (lock step) */
 };
 
 struct Api
@@ -201,7 +202,7 @@ void emit_xform(std::ostringstream &o, Pool<T> &pool, const std::string &name, i
     o << "    for (int i = 0; i < JD; ++i) v[i] = 0.0;\n";
     o << "    PolarT<T> P; P.r2 = P.r = P.ang = P.sa = P.ca = 0.0;\n";
     if (D == 2)
-        o << "    polar_fill(P," << xf.need << "u,t[0],t[1]);\n";
+        o << "    JPOLAR(P," << xf.need << "u,t[0],t[1]);\n";
     for (uint32_t k = xf.var_begin; k < xf.var_begin + xf.var_count; ++k)
     {
         const DevVarT<T> &var = vars[k];
@@ -220,7 +221,7 @@ void emit_xform(std::ostringstream &o, Pool<T> &pool, const std::string &name, i
             {
                 /* VariationFrom2D::calc_h, variations.hpp:94-105 */
                 o << "        const T a0 = t[" << var.axis_x << "], a1 = t[" << var.axis_y << "];\n";
-                o << "        polar_fill(P," << var.need << "u,a0,a1);\n";
+                o << "        JPOLAR(P," << var.need << "u,a0,a1);\n";
             }
             else
                 o << "        const T a0 = t[0], a1 = t[1];\n";
@@ -284,6 +285,10 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
     for (int i = 0; i < 16; ++i)
         h << (i ? "," : "") << m0_32[i] << "u";
     h << "}\n";
+    if (cfg.async)
+        h << "#define FFR_SINCOS_OOL 1\n#define JPOLAR(P,need,x,y) P = polar_fill_ool<JT>(need,x,y)\n";
+    else
+        h << "#define JPOLAR(P,need,x,y) polar_fill(P,need,x,y)\n";
     h << "#include \"ffr_params.cuh\"\n";
     h << "typedef " << (sizeof(T) == 8 ? "double" : "float") << " JT;\n";
     h << "#define JD " << D << "\n#define JR " << R << "\n#define JNX " << NX << "\n#define JNS " << cfg.ns
@@ -310,6 +315,23 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
     o << "__device__ __forceinline__ unsigned jit_select(JT r)\n{\n    unsigned i = 0;\n";
     for (int k = 0; k + 1 < NX; ++k)
         o << "    i += (" << pool.ref(fl->xfcw[k]) << " < r) ? 1u : 0u;\n";
+    o << "    return i;\n}\n\n";
+    /* the same selection straight from a generator word: randNum() = m / 2^b with m = word >> s
+       (b = 53, s = 11 for u64; b = 24, s = 8 for u32, flame_rng.hpp:67-87), and xfcw[k] < m / 2^b
+       <=> m > floor(xfcw[k] * 2^b) for integer m (scaling by 2^b is exact), so the integer compare
+       selects exactly what the floating point compare selects */
+    o << "__device__ __forceinline__ unsigned jit_select_word(Real<JT>::word w)\n{\n    unsigned i = 0;\n"
+      << "    const Real<JT>::word m = w >> " << (sizeof(T) == 8 ? 11 : 8) << ";\n";
+    for (int k = 0; k + 1 < NX; ++k)
+    {
+        const double scaled = std::floor(std::ldexp((double)fl->xfcw[k],sizeof(T) == 8 ? 53 : 24));
+        const unsigned long long thr = scaled >= 18446744073709549568.0 ? ~0ULL :
+            (scaled <= 0.0 ? 0ULL : (unsigned long long)scaled);
+        if (fl->xfcw[k] < (T)0)
+            o << "    i += 1u;\n";     /* a negative table entry is below every r */
+        else
+            o << "    i += (m > (Real<JT>::word)" << thr << "ULL) ? 1u : 0u;\n";
+    }
     o << "    return i;\n}\n\n";
     o << "__device__ __forceinline__ bool jit_inb(const JT *pf)\n{\n    bool inb = true;\n";
     for (int i = 0; i < D; ++i)
@@ -341,7 +363,7 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
     for (int k = 0; k < NX; ++k)
         o << "    case " << k << ": return " << xfs[k].json_id << "ULL;\n";
     o << "    default: return 0;\n    }\n}\n\n";
-    o << "#include \"ffr_jit_kernel.cuh\"\n";
+    o << "#include \"" << (cfg.async ? "ffr_jit_async.cuh" : "ffr_jit_kernel.cuh") << "\"\n";
     h << "__constant__ JT jc[" << (pool.vals.empty() ? 1 : pool.vals.size()) << "] = {";
     for (size_t i = 0; i < pool.vals.size(); ++i)
         h << (i ? "," : "") << lit(pool.vals[i]);
@@ -393,6 +415,7 @@ inline const std::vector<Shim> &headers()
         {"ffr_device.cuh",(const char*)ffr_embed_device,ffr_embed_device_len},
         {"ffr_params.cuh",(const char*)ffr_embed_params,ffr_embed_params_len},
         {"ffr_jit_kernel.cuh",(const char*)ffr_embed_jit_kernel,ffr_embed_jit_kernel_len},
+        {"ffr_jit_async.cuh",(const char*)ffr_embed_jit_async,ffr_embed_jit_async_len},
         {"../../include/ffr_cuda.h",(const char*)ffr_embed_abi,ffr_embed_abi_len},
         {"cstdint",shim_int,sizeof(shim_int)-1},
         {"stdint.h",shim_int,sizeof(shim_int)-1},
@@ -461,21 +484,51 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
     std::vector<std::string> texts;
     for (const Shim &s : headers())
         texts.emplace_back(s.text,s.len);     /* NUL-terminated copies */
-    for (size_t i = 0; i < texts.size(); ++i)
+    /* FFR_JIT_DUMP_DIR (profiling aid): compile from real files so that -lineinfo points at
+       paths ncu --import-source can read: <dir>/p/csrc/ffr_flame.cu + headers */
+    std::string prog_name = "ffr_flame.cu", inc_opt;
+    const char *dump = getenv("FFR_JIT_DUMP_DIR");
+    if (dump && *dump)
     {
-        hn.push_back(headers()[i].name);
-        ht.push_back(texts[i].c_str());
+        const std::string d = dump;
+        mkdir(d.c_str(),0755);
+        mkdir((d + "/p").c_str(),0755);
+        mkdir((d + "/p/csrc").c_str(),0755);
+        mkdir((d + "/include").c_str(),0755);
+        auto put = [](const std::string &path, const std::string &text)
+        {
+            if (FILE *f = fopen(path.c_str(),"wb"))
+            {
+                fwrite(text.data(),1,text.size(),f);
+                fclose(f);
+            }
+        };
+        for (size_t i = 0; i < texts.size(); ++i)
+        {
+            const std::string nm = headers()[i].name;
+            put(nm.rfind("../../",0) == 0 ? d + "/" + nm.substr(6) : d + "/p/csrc/" + nm,texts[i]);
+        }
+        prog_name = d + "/p/csrc/ffr_flame.cu";
+        put(prog_name,src);
+        inc_opt = "-I" + d + "/p/csrc";
     }
+    else
+        for (size_t i = 0; i < texts.size(); ++i)
+        {
+            hn.push_back(headers()[i].name);
+            ht.push_back(texts[i].c_str());
+        }
     timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC,&t0);
     nvrtcProgram prog = nullptr;
-    if (a.CreateProgram(&prog,src.c_str(),"ffr_flame.cu",(int)hn.size(),ht.data(),hn.data()) != NVRTC_SUCCESS)
+    if (a.CreateProgram(&prog,src.c_str(),prog_name.c_str(),(int)hn.size(),ht.data(),hn.data()) != NVRTC_SUCCESS)
     {
         err = "nvrtcCreateProgram failed";
         return false;
     }
-    const char *opts[] = {"--gpu-architecture=sm_100a","-fmad=false","-std=c++17","-lineinfo","-default-device"};
-    const nvrtcResult rc = a.CompileProgram(prog,5,opts);
+    const char *opts[] = {"--gpu-architecture=sm_100a","-fmad=false","-std=c++17","-lineinfo","-default-device",
+        inc_opt.c_str()};
+    const nvrtcResult rc = a.CompileProgram(prog,inc_opt.empty() ? 5 : 6,opts);
     if (rc != NVRTC_SUCCESS)
     {
         size_t n = 0;

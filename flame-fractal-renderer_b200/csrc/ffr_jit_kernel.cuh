@@ -166,7 +166,7 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
             const int slot = s0 + tid;
             const u64 kk = g*JNS + slot;
             unsigned key = JKEY_NONE;
-            if (kk < prm.chain_count)
+            if (slot < JNS && kk < prm.chain_count)
             {
                 RngT<T> rng;
                 rng.col = rng_base + slot;

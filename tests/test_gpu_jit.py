@@ -54,7 +54,7 @@ EXAMPLES_2D = ["barnsley_fern", "csci6360_project", "flam3_test_1", "rectangle_m
 def test_examples_bit_exact_vs_interpreter(ffr, examples, name):
     st, info = compare(ffr, examples.example_json(name, size=[160, 120]))
     assert st["s_iter"] == 699 * 300 + 77
-    assert info["slots_per_block"] % info["threads_per_block"] == 0
+    assert info["slots_per_block"] >= info["threads_per_block"] and info["registers"] > 0
 
 
 def test_3d_example_and_float_build(ffr, examples):
