@@ -175,7 +175,7 @@ struct ffr_ctx
     jit::Config jit_cfg;
     size_t jit_smem = 0;
     double jit_compile_s = 0.0;
-    std::string jit_source, jit_err;
+    std::string jit_source, jit_err, jit_note;
     std::vector<char> jit_cubin;
 };
 
@@ -563,6 +563,8 @@ bool jit_prepare(ffr_ctx *ctx)
     if (!ctx->jit_cubin.empty())
         return true;
     jit::Config &cfg = ctx->jit_cfg;
+    const bool uses_rng = ctx->elem == 8 ? ((const DevFlameT<double>*)ctx->blob.data())->uses_rng != 0
+                                         : ((const DevFlameT<float>*)ctx->blob.data())->uses_rng != 0;
     cfg.async = env_int("FFR_JIT_ASYNC",1) != 0;
     cfg.tpb = env_int("FFR_JIT_TPB",cfg.async ? 320 : 256);
     cfg.minb = env_int("FFR_JIT_MINB",2);
@@ -571,47 +573,61 @@ bool jit_prepare(ffr_ctx *ctx)
        Per slot: ISAAC randmem[16] + randa/b/c/cnt, the point, the colour, then K1d: 16 packed
        selections, iteration and chain numbers + one ring entry per queue; K1c: two queue entries per xform */
     const size_t per_slot = (size_t)20*ctx->elem + (size_t)(ctx->dims + ctx->r)*ctx->elem +
-        (cfg.async ? 16u + 2u*(ctx->num_xforms + 1u) : 4u*ctx->num_xforms);
+        (cfg.async ? 16u : 4u*ctx->num_xforms) + (cfg.async && uses_rng ? (size_t)16*ctx->elem : 0u);
+    const size_t nq = ctx->num_xforms + 1u;
+    auto pow2ceil = [](int v) { int p = 64; while (p < v) p *= 2; return p; };
+    auto smem_for = [&](int n) { return per_slot*(size_t)n + (cfg.async ? 2u*nq*(size_t)pow2ceil(n) : 0u); };
     int ns = env_int("FFR_JIT_NS",0);
     if (ns <= 0)
     {
         const size_t budget = (227u*1024u)/(size_t)cfg.minb - 2048u;
-        ns = (int)(budget/per_slot);
-        if (ns > 1024) ns = 1024;
+        ns = 1024;
+        while (ns > 64 && smem_for(ns) > budget)
+            ns -= 32;
         if (!cfg.async)
             ns -= ns % cfg.tpb;
     }
-    if (cfg.async)
-    {
-        int p2 = 64;
-        while (p2*2 <= ns) p2 *= 2;
-        ns = p2;             /* ring index = position & (ns-1) */
-        if (!getenv("FFR_JIT_TPB"))
-        {
-            /* keep >= 32 slots per queue out of flight so that full chunks can always be popped */
-            int t = ns - 32*((int)ctx->num_xforms + 1);
-            t -= t % 32;
-            cfg.tpb = std::max(128,std::min(cfg.tpb,t));
-        }
-    }
     ns -= ns % 32;       /* whole warps seed the slots */
+    if (cfg.async && !getenv("FFR_JIT_TPB"))
+    {
+        /* keep >= 32 slots per queue out of flight so that full chunks can always be popped */
+        int t = ns - 32*(int)nq;
+        t -= t % 32;
+        cfg.tpb = std::max(128,std::min(cfg.tpb,t));
+    }
     if (ns < 64 || ns > 32768 || cfg.tpb < 64 || cfg.tpb % 32 || cfg.tpb > 1024)
     {
         ctx->jit_err = "K1c: no valid slot count for this flame";
         return false;
     }
     cfg.ns = ns;
-    ctx->jit_smem = per_slot*(size_t)ns;
+    cfg.cap = pow2ceil(ns);
+    ctx->jit_smem = smem_for(ns);
     u64 m0[16];
     unsigned int m0_32[16];
     isaac_m0(m0);
     isaac_m0_32(m0_32);
-    ctx->jit_source = ctx->elem == 8 ? jit::generate<double>(ctx->blob,ctx->colors,m0,m0_32,cfg)
-                                     : jit::generate<float>(ctx->blob,ctx->colors,m0,m0_32,cfg);
-    if (!jit::compile(ctx->jit_source,ctx->jit_cubin,ctx->jit_err,&ctx->jit_compile_s,&ctx->jit_cached))
+    for (int attempt = 0; attempt < 2; ++attempt)
     {
-        ctx->jit_cubin.clear();
-        return false;
+        ctx->jit_source = ctx->elem == 8 ? jit::generate<double>(ctx->blob,ctx->colors,m0,m0_32,cfg)
+                                         : jit::generate<float>(ctx->blob,ctx->colors,m0,m0_32,cfg);
+        long spills = 0;
+        double secs = 0.0;
+        if (!jit::compile(ctx->jit_source,ctx->jit_cubin,ctx->jit_err,&secs,&ctx->jit_cached,&spills))
+        {
+            ctx->jit_cubin.clear();
+            return false;
+        }
+        ctx->jit_compile_s += secs;
+        ctx->jit_note += "tpb " + std::to_string(cfg.tpb) + ": " + std::to_string(spills) + " spill bytes; ";
+        /* 320 threads x 2 blocks cap the kernel at 96 registers; a flame whose xforms spill there
+           runs faster with 256 threads (128 registers) than with spills through a thrashed L1 */
+        if (attempt == 0 && spills > 0 && cfg.tpb > 256 && !getenv("FFR_JIT_TPB"))
+        {
+            cfg.tpb = 256;
+            continue;
+        }
+        break;
     }
     return true;
 }
@@ -1494,7 +1510,7 @@ int ffr_cuda_jit_info(const ffr_ctx *ctx, ffr_jit_info *info)
     info->cubin_bytes = (uint64_t)ctx->jit_cubin.size();
     info->source_bytes = (uint64_t)ctx->jit_source.size();
     info->compile_seconds = ctx->jit_compile_s;
-    snprintf(info->message,sizeof(info->message),"%s",ctx->jit_err.c_str());
+    snprintf(info->message,sizeof(info->message),"%s",ctx->jit_err.empty() ? ctx->jit_note.c_str() : ctx->jit_err.c_str());
     return FFR_OK;
 }
 

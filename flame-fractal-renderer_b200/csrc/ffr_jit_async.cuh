@@ -28,14 +28,14 @@ with one warp-aggregated atomicAdd on the tail and then write the entries; consu
 range with a CAS on the head and wait for each claimed entry to become valid (a producer that
 reserved a position writes it a few instructions later and waits for nothing in between).
 At most JNS entries are ever reserved-and-unread over all queues (one per slot), so a ring of
-JNS entries cannot overrun.
+JCAP >= JNS entries cannot overrun.
 
 Which warp advances a chain, and in which order chains interleave, changes neither a chain's
 stream nor its arithmetic: histogram counts and statistics equal K1/K1b/K1c bit for bit
 (tests/test_gpu_jit.py).
 
 The generated translation unit defines, before including this file, what ffr_jit_kernel.cuh
-lists; JNS is a power of two here.
+lists, plus JCAP.
 */
 
 #pragma once
@@ -47,7 +47,7 @@ lists; JNS is a power of two here.
 #define JNQ (JNX + 1)            /* xform queues + the gen() queue */
 #define JQ_GEN JNX
 #define JEMPTY 0xffffu
-#define JMASK (JNS - 1)
+#define JMASK (JCAP - 1)          /* JCAP: ring capacity, the power of two >= JNS */
 #define JABORT_WATCHDOG 0x100u
 typedef Real<JT>::word JW;
 
@@ -136,7 +136,7 @@ __device__ __noinline__ unsigned long long jit_keys_from_rsl(const JW *rcol)
     unsigned long long keys = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-        keys |= (unsigned long long)jit_select_word(rcol[i*JNS]) << (4*i);
+        keys |= (unsigned long long)jit_select_word(FFR_RSL_LOAD(&rcol[i*JNS])) << (4*i);
     return keys;
 }
 
@@ -157,8 +157,12 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
     unsigned long long *s_keys = (unsigned long long*)(sc + JR*JNS);  /* 16 packed selections */
     int *s_it = (int*)(s_keys + JNS);                /* iteration number of the slot's chain */
     unsigned int *s_chain = (unsigned int*)(s_it + JNS);  /* chain index within this launch */
-    unsigned short *ring = (unsigned short*)(s_chain + JNS);  /* [JNQ][JNS] */
-    W *rsl_base = (W*)prm.rsl_scratch + (size_t)blockIdx.x*16*JNS;  /* randrsl: L2-resident */
+    unsigned short *ring = (unsigned short*)(s_chain + JNS);  /* [JNQ][JCAP] */
+#if JRSL_SMEM
+    W *rsl_base = (W*)(ring + JNQ*JCAP);             /* randrsl columns (flames with drawing variations) */
+#else
+    W *rsl_base = (W*)prm.rsl_scratch + (size_t)blockIdx.x*16*JNS;  /* randrsl: L2-resident scratch */
+#endif
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -184,7 +188,7 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
         pmax[i] = -INFINITY;
     }
 
-    for (int i = tid; i < JNQ*JNS; i += JTPB)
+    for (int i = tid; i < JNQ*JCAP; i += JTPB)
         ring[i] = (unsigned short)JEMPTY;
     if (tid < JNQ)
     {
@@ -199,7 +203,7 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
 
     /* Shared tail of every step: lanes flagged `fresh` take a new chain (or retire their slot),
        then every lane with a key queues its slot. Called by all 32 lanes, converged. */
-#define JIT_START_AND_PUSH(fresh,slot,key,wrote_global) do { \
+#define JIT_START_AND_PUSH(fresh,slot,key) do { \
         const unsigned fm_ = __ballot_sync(0xffffffffu,(fresh)); \
         if (fm_) \
         { \
@@ -250,17 +254,17 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
             if ((key) < JNQ && rank_ == 0) \
                 pos_ = atomicAdd(&s_ht[key].y,(unsigned)__popc(peers_)); \
             pos_ = __shfl_sync(0xffffffffu,pos_,leader_); \
-            /* the slot's state must be visible before its queue entry. Shared-memory stores of \
-               one thread are performed in program order, so the hot path needs only to stop the \
-               compiler from reordering; a real fence would also wait for the scatter REDs just \
-               issued (measured: 2x slower). Only steps that wrote generator words to the \
-               global scratch (gen(), seeding) pay for the fence. */ \
-            if (fm_ || (wrote_global)) \
-                __threadfence_block(); \
-            else \
-                asm volatile("" ::: "memory"); \
+            /* The slot's state must be visible before its queue entry. Shared-memory stores of \
+               one thread are performed in program order, so the compiler is all that has to be \
+               kept from reordering. NO memory fence anywhere in this kernel: with a MEMBAR in \
+               the code ptxas turns every scatter RED into an ATOMG whose (discarded) return \
+               value the warp then waits for -- measured 2x on the colour flames. Generator \
+               words that other warps may read go to shared memory when the flame has drawing \
+               variations (JRSL_SMEM); otherwise the global scratch is only read by cold paths \
+               many steps after the gen() that wrote it, with L1-bypassing loads. */ \
+            asm volatile("" ::: "memory"); \
             if ((key) < JNQ) \
-                *(volatile unsigned short*)&ring[(key)*JNS + ((pos_ + rank_) & JMASK)] = (unsigned short)(slot); \
+                *(volatile unsigned short*)&ring[(key)*JCAP + ((pos_ + rank_) & JMASK)] = (unsigned short)(slot); \
         } \
     } while (0)
 
@@ -270,18 +274,26 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
         const int slot = s0 + tid;
         const bool fresh = slot < JNS;
         unsigned key = JKEY_NONE;
-        JIT_START_AND_PUSH(fresh,slot,key,true);
+        JIT_START_AND_PUSH(fresh,slot,key);
     }
 
     unsigned long long spins = 0;
+#ifdef JROT_STATIC
+    /* warps that share a scheduler (warp index mod 4) prefer the same queues, so that its
+       instruction cache holds fewer xform bodies */
+    unsigned rot = (((unsigned)(tid >> 5) & 3u)*(unsigned)JNQ) >> 2;
+#else
     unsigned rot = (unsigned)(tid >> 5);
+#endif
     for (;;)
     {
         /* ---- pop up to 32 slots: the first queue holding >= 32, scanning from a position that
            rotates per warp and step so that warps spread over the queues ---- */
         unsigned q = JKEY_NONE, h0 = 0, n = 0;
         int fails = 0;
+#ifndef JROT_STATIC
         ++rot;
+#endif
         for (;;)
         {
             unsigned av = 0, hd = 0;
@@ -340,7 +352,7 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
         unsigned slot = 0;
         if (act)
         {
-            volatile unsigned short *e = &ring[q*JNS + ((h0 + lane) & JMASK)];
+            volatile unsigned short *e = &ring[q*JCAP + ((h0 + lane) & JMASK)];
             unsigned v = *e;
             unsigned long long w = 0;
             while (v == JEMPTY && ++w < (1ULL << 28))
@@ -563,7 +575,7 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
                 }
             }
         }
-        JIT_START_AND_PUSH(fresh,slot,newkey,q == JQ_GEN || JANY_RNG);
+        JIT_START_AND_PUSH(fresh,slot,newkey);
     }
 #undef LOAD_ABC
 #undef STORE_ABC

@@ -37,7 +37,8 @@ namespace jit
 struct Config
 {
     int tpb = 256;          /* threads per block */
-    int ns = 512;           /* chain slots per block (multiple of tpb) */
+    int ns = 512;           /* chain slots per block */
+    int cap = 512;          /* K1d: ring capacity, power of two >= ns */
     int minb = 2;           /* blocks per SM asked of ptxas (register cap) */
     bool inline_math = false;
     bool async = true;      /* K1d (ffr_jit_async.cuh, queue scheduled) instead of K1c (lock step) */
@@ -274,7 +275,7 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
     const int D = (int)fl->dims, R = (int)fl->r, NX = (int)fl->num_xforms;
     std::ostringstream h, o;   /* head (needs the finished constant pool) and body */
     Pool<T> pool;
-    h << "/* generated by libffr_cuda for one flame: K1c, see ffr_jit_kernel.cuh */\n";
+    h << "/* generated by libffr_cuda for one flame (ffr_jit_host.cuh); kernel: " << (cfg.async ? "ffr_jit_async.cuh" : "ffr_jit_kernel.cuh") << " */\n";
     h << "#define FFR_TPB " << cfg.ns << "\n";
     if (cfg.inline_math)
         h << "#define FFR_MATH_ATTR __forceinline__\n";
@@ -285,6 +286,11 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
     for (int i = 0; i < 16; ++i)
         h << (i ? "," : "") << m0_32[i] << "u";
     h << "}\n";
+    if (getenv("FFR_JIT_ROT_STATIC") && *getenv("FFR_JIT_ROT_STATIC") == '1')
+        h << "#define JROT_STATIC 1\n";
+    if (cfg.async)
+        h << "#define JRSL_SMEM " << (fl->uses_rng ? 1 : 0) << "\n"
+          << (fl->uses_rng ? "" : "#define FFR_RSL_LOAD(p) __ldcg(p)\n");
     if (cfg.async)
         h << "#define FFR_SINCOS_OOL 1\n#define JPOLAR(P,need,x,y) P = polar_fill_ool<JT>(need,x,y)\n";
     else
@@ -292,6 +298,7 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
     h << "#include \"ffr_params.cuh\"\n";
     h << "typedef " << (sizeof(T) == 8 ? "double" : "float") << " JT;\n";
     h << "#define JD " << D << "\n#define JR " << R << "\n#define JNX " << NX << "\n#define JNS " << cfg.ns
+      << "\n#define JCAP " << cfg.cap
       << "\n#define JTPB " << cfg.tpb << "\n#define JMINB " << cfg.minb << "\n#define JHAS_FINAL "
       << (fl->has_final ? 1 : 0) << "\n#define JANY_RNG " << (fl->uses_rng ? 1 : 0) << "\n\n";
     for (int k = 0; k < NX + (fl->has_final ? 1 : 0); ++k)
@@ -427,9 +434,20 @@ inline const std::vector<Shim> &headers()
 
 /* source -> sm_100a cubin. Needs no GPU. */
 inline bool compile(const std::string &src, std::vector<char> &cubin, std::string &err, double *seconds,
-        bool *from_cache)
+        bool *from_cache, long *spill_bytes)
 {
+    /* the last 8 bytes of a cached entry hold the kernel's register spill bytes (ptxas -v) */
     static std::map<u64,std::vector<char>> mem_cache;
+    auto split = [&](std::vector<char> &blob)
+    {
+        long long sp = 0;
+        if (blob.size() >= 8)
+        {
+            memcpy(&sp,blob.data() + blob.size() - 8,8);
+            blob.resize(blob.size() - 8);
+        }
+        if (spill_bytes) *spill_bytes = (long)sp;
+    };
     static std::mutex mu;
     Api &a = api(false);
     if (seconds) *seconds = 0.0;
@@ -452,6 +470,7 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
         if (it != mem_cache.end())
         {
             cubin = it->second;
+            split(cubin);
             if (from_cache) *from_cache = true;
             return true;
         }
@@ -475,6 +494,7 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
             {
                 std::lock_guard<std::mutex> lock(mu);
                 mem_cache[h] = cubin;
+                split(cubin);
                 if (from_cache) *from_cache = true;
                 return true;
             }
@@ -527,14 +547,17 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
         return false;
     }
     const char *opts[] = {"--gpu-architecture=sm_100a","-fmad=false","-std=c++17","-lineinfo","-default-device",
-        inc_opt.c_str()};
-    const nvrtcResult rc = a.CompileProgram(prog,inc_opt.empty() ? 5 : 6,opts);
-    if (rc != NVRTC_SUCCESS)
+        "--ptxas-options=-v",inc_opt.c_str()};
+    const nvrtcResult rc = a.CompileProgram(prog,inc_opt.empty() ? 6 : 7,opts);
+    std::string log;
     {
         size_t n = 0;
         a.GetProgramLogSize(prog,&n);
-        std::string log(n,'\0');
+        log.assign(n,'\0');
         if (n) a.GetProgramLog(prog,&log[0]);
+    }
+    if (rc != NVRTC_SUCCESS)
+    {
         err = "NVRTC: " + log.substr(0,4000);
         a.DestroyProgram(&prog);
         return false;
@@ -544,6 +567,25 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
     cubin.resize(n);
     a.GetCUBIN(prog,cubin.data());
     a.DestroyProgram(&prog);
+    /* "Function properties for ffr_jit_render ... N bytes spill stores" */
+    long long spills = 0;
+    {
+        size_t at = log.find("Function properties for ffr_jit_render");
+        if (at != std::string::npos)
+        {
+            size_t e = log.find("bytes spill stores",at);
+            if (e != std::string::npos)
+            {
+                size_t b = log.rfind(',',e);
+                if (b != std::string::npos && b > at)
+                    spills = atoll(log.c_str() + b + 1);
+            }
+        }
+    }
+    if (spill_bytes) *spill_bytes = (long)spills;
+    std::vector<char> entry = cubin;
+    entry.resize(cubin.size() + 8);
+    memcpy(entry.data() + cubin.size(),&spills,8);
     clock_gettime(CLOCK_MONOTONIC,&t1);
     if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9*(double)(t1.tv_nsec - t0.tv_nsec);
     if (!(nocache && *nocache == '1'))
@@ -552,14 +594,14 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
         const std::string tmp = path + "." + std::to_string((long)getpid());
         if (FILE *f = fopen(tmp.c_str(),"wb"))
         {
-            const bool ok = fwrite(cubin.data(),1,cubin.size(),f) == cubin.size();
+            const bool ok = fwrite(entry.data(),1,entry.size(),f) == entry.size();
             fclose(f);
             if (!ok || rename(tmp.c_str(),path.c_str()) != 0)
                 unlink(tmp.c_str());
         }
     }
     std::lock_guard<std::mutex> lock(mu);
-    mem_cache[h] = cubin;
+    mem_cache[h] = entry;
     return true;
 }
 

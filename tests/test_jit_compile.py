@@ -15,7 +15,7 @@ def test_generate_and_compile_without_device(ffr, examples):
     assert n > 10000
     for k in range(6):
         assert "jx_%d(" % k in src            # 5 xforms + the final xform, one function each
-    assert "__constant__ JT jc[" in src and '#include "ffr_jit_kernel.cuh"' in src
+    assert "__constant__ JT jc[" in src and '#include "ffr_jit_async.cuh"' in src
     # literals are hexadecimal floating point: exactly the blob's values
     assert "0x1.ccccccccccccdp-1" in src      # 0.9
 

@@ -40,9 +40,9 @@ def main():
             n = chains * L
             ji = r.jit_info
             print("%-10s mode %d rg %d jit %d  %.3e samples in %.3fs = %.3e samples/s  plotted %.3f  "
-                  "[create %.2fs regs %d slots %d bps %d]" % (
+                  "[create %.2fs regs %d slots %d bps %d] %s" % (
                 nm, mode, rg, jit, n, dt, n / dt, st["s_plot"] / st["s_iter"], tc, ji["registers"],
-                ji["slots_per_block"], ji["blocks_per_sm"]), flush=True)
+                ji["slots_per_block"], ji["blocks_per_sm"], ji["message"]), flush=True)
             r.close()
 
 if __name__ == "__main__":
