@@ -186,6 +186,9 @@ def main():
                     help="bounded CPU sample per step for the reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scatter", type=int, default=0)
+    ap.add_argument("--jit", type=int, default=-1,
+                    help="run-time compiled flame-specialised kernel: -1 = on for flames with "
+                         "non-linear variations, 1 = off (interpreter kernels), 2 = on")
     args = ap.parse_args()
     wl_name = args.workload
     if args.impl == "reference":
@@ -222,8 +225,16 @@ def main():
     # a dedicated (non-default) stream: handle 0 would mean "library-owned stream" to the ABI
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
+    # the flame-specialised kernel is compiled (NVRTC, cached) when the context is created, i.e.
+    # outside every timed region, like the ahead-of-time build of the interpreter kernels
+    jit = args.jit
+    if jit < 0:
+        jit = ffr.JIT_OFF if flame.uses_only([1]) else ffr.JIT_ON   # op 1 = linear
+    t_create = time.perf_counter()
     rend = ffr.BufferRenderer(flame, devices=[local_rank], external_buffer=buf.data_ptr(),
-                              stream=stream.cuda_stream, scatter_mode=args.scatter)
+                              stream=stream.cuda_stream, scatter_mode=args.scatter, jit=jit)
+    t_create = time.perf_counter() - t_create
+    jit_info = rend.jit_info
     # one wave = every resident block (SMs x blocks/SM) takes one chain group of 256 chains
     chains_per_step = rend.resident_chains * args.waves
     samples_per_step = chains_per_step * L
@@ -297,7 +308,7 @@ def main():
 
     # ---- e2e through the C ABI with host buffers ----
     rend.close()
-    e2e_rend = ffr.BufferRenderer(flame, devices=[local_rank])
+    e2e_rend = ffr.BufferRenderer(flame, devices=[local_rank], jit=jit)
     nbytes = n_elems * 8
     host_in = torch.zeros(n_elems, dtype=torch.int64).pin_memory()
     host_out = torch.zeros(n_elems, dtype=torch.int64).pin_memory()
@@ -309,7 +320,7 @@ def main():
         e2e_rend.close()
         ebuf = torch.zeros(n_elems, dtype=torch.int64, device=dev)
         e2e_rend = ffr.BufferRenderer(flame, devices=[local_rank], external_buffer=ebuf.data_ptr(),
-                                      stream=stream.cuda_stream)
+                                      stream=stream.cuda_stream, jit=jit)
 
         def e2e_step(k):
             ebuf.zero_()
@@ -371,6 +382,14 @@ def main():
             "config": {"workload": wl_name, "flame": ename, "size": size, "color_dims": r_dims,
                        "chain_len": L, "chains_per_step_per_gpu": chains_per_step,
                        "samples_per_step_per_gpu": samples_per_step, "base_seed": 1,
+                       "kernel": ("flame-specialised, compiled at context creation (NVRTC %.1f s%s, "
+                                  "context %.1f s): %d threads x %d blocks/SM, %d chain slots/block, "
+                                  "%d registers; %s" % (jit_info["compile_seconds"],
+                                                    ", cached" if jit_info["from_cache"] else "",
+                                                    t_create, jit_info["threads_per_block"],
+                                                    jit_info["blocks_per_sm"], jit_info["slots_per_block"],
+                                                    jit_info["registers"], jit_info["message"].strip())
+                                  if jit_info["active"] else "ahead-of-time interpreter kernel"),
                        "parallelism": "chain-range sharding x%d, private buffers, "
                                       "final NCCL sum-reduce" % world,
                        "l2": "no flush: the only memory operand is the %.0f MiB accumulation "

@@ -676,7 +676,8 @@ void jit_maybe(ffr_ctx *ctx, u64 samples)
     if (ctx->jit_ready || ctx->jit_failed || !ctx->jit_eligible || ctx->jit_mode != 0)
         return;
     const char *e = getenv("FFR_JIT_MIN_SAMPLES");
-    const double min_samples = (e && *e) ? atof(e) : 2e10;
+    /* ~2 s of NVRTC against ~4e-11 s saved per sample over the interpreter kernels */
+    const double min_samples = (e && *e) ? atof(e) : 5e10;
     if ((double)samples >= min_samples)
         jit_activate(ctx);
 }
@@ -907,9 +908,9 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
         if (rc != FFR_OK)
             return fail(ctx->err);
     }
-    /* K1c (run-time compiled). opt.jit: 0 auto = compiled lazily by the first render call of
-       >= FFR_JIT_MIN_SAMPLES samples, for flames the divergence model sends to K1b; 1 never;
-       2 now, for any flame K1c supports. FFR_JIT=0/1 in the environment overrides auto. */
+    /* K1c/K1d (run-time compiled). opt.jit: 0 auto = compiled lazily by the first render call of
+       >= FFR_JIT_MIN_SAMPLES samples, for flames with variations other than linear; 1 never;
+       2 now, for any flame the kernel supports. FFR_JIT=0/1 in the environment overrides auto. */
     ctx->jit_mode = ctx->opt.jit;
     if (ctx->jit_mode == 0)
     {
@@ -917,7 +918,7 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
         if (e && *e == '0') ctx->jit_mode = 1;
         else if (e && *e == '1') ctx->jit_mode = 2;
     }
-    ctx->jit_eligible = ctx->jit_mode != 1 && jit_supported(ctx) && (ctx->jit_mode == 2 || ctx->regroup);
+    ctx->jit_eligible = ctx->jit_mode != 1 && jit_supported(ctx) && (ctx->jit_mode == 2 || !ctx->affine_only);
     if (ctx->jit_mode == 2 && ctx->opt.jit == 2)
     {
         if (!ctx->jit_eligible)

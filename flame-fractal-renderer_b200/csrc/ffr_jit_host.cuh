@@ -69,7 +69,7 @@ struct Api
 inline void *open_first(const char *const *names)
 {
     for (; *names; ++names)
-        if (void *h = dlopen(*names,RTLD_NOW|RTLD_GLOBAL))
+        if (void *h = dlopen(*names,RTLD_NOW|RTLD_LOCAL))
             return h;
     return nullptr;
 }
@@ -83,8 +83,10 @@ inline Api &api(bool need_driver)
     if (!a.tried)
     {
         a.tried = true;
-        static const char *const rtc[] = {"libnvrtc.so.12","libnvrtc.so",
-            "/usr/local/cuda/lib64/libnvrtc.so.12","/usr/local/cuda/lib64/libnvrtc.so",nullptr};
+        /* the toolkit's compiler first (the one the ahead-of-time kernels were built with); a
+           host process may have another libnvrtc.so.12 loaded already (PyTorch bundles one) */
+        static const char *const rtc[] = {"/usr/local/cuda/lib64/libnvrtc.so.12","/usr/local/cuda/lib64/libnvrtc.so",
+            "libnvrtc.so.12","libnvrtc.so",nullptr};
         void *h = open_first(rtc);
         if (!h)
         {
