@@ -56,7 +56,8 @@ UNIT = "samples/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per PLOTTED sample of the render kernel, from the
 # committed `ncu --set full` captures (profiles/README.md); traffic per launch = this x plotted
 NCU_DRAM_BYTES_PER_PLOTTED = {
-    "csci6360_4096": (0.2489e9 + 2.2624e9) / 492.7e6,   # profiles/r1_render_regroup_csci4096
+    "csci6360_4096": (0.2551e9 + 1.9064e9) / 261.7e6,   # profiles/r1_k1d_csci4096 (329.8e6 samples)
+    "tkoz_test3_4096": (1.8337e9 + 6.6085e9) / 327.7e6,  # profiles/r1_k1d_tkoz3_4096
     "sierpinski3d_512": (8.46e6 + 0.535e6) / 620.8e6,   # profiles/r1_render_affine_sierp3d
 }
 

@@ -622,7 +622,7 @@ bool jit_prepare(ffr_ctx *ctx)
         ctx->jit_note += "tpb " + std::to_string(cfg.tpb) + ": " + std::to_string(spills) + " spill bytes; ";
         /* 320 threads x 2 blocks cap the kernel at 96 registers; a flame whose xforms spill there
            runs faster with 256 threads (128 registers) than with spills through a thrashed L1 */
-        if (attempt == 0 && spills > 128 && cfg.tpb > 256 && !getenv("FFR_JIT_TPB"))
+        if (attempt == 0 && spills > 32 && cfg.tpb > 256 && !getenv("FFR_JIT_TPB"))
         {
             cfg.tpb = 256;
             continue;
