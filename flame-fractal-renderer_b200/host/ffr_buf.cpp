@@ -55,7 +55,9 @@ static void usage()
         "  -z [ --bad-values ] arg (=256) bad values limit\n"
         "  --seed arg                    base seed (default: from the clock)\n"
         "  --gpus arg (=1)               GPUs to use\n"
-        "  --float                       float/uint32_t build (4-byte buffer elements)\n";
+        "  --float                       float/uint32_t build (4-byte buffer elements)\n"
+        "  --jit / --no-jit              compile a kernel for this flame at start-up (NVRTC) / never;\n"
+        "                                default: only for renders large enough to repay the compile\n";
 }
 
 static bool read_all(std::istream& is, std::string& out)
@@ -96,6 +98,7 @@ int main(int argc, char **argv)
     bool have_seed = false;
     int arg_gpus = 1;
     int arg_elem = 8;
+    uint32_t arg_jit = 0;
 
     static const struct option longopts[] = {
         {"help",no_argument,nullptr,'h'},
@@ -109,6 +112,8 @@ int main(int argc, char **argv)
         {"seed",required_argument,nullptr,1000},
         {"gpus",required_argument,nullptr,1001},
         {"float",no_argument,nullptr,1002},
+        {"jit",no_argument,nullptr,1003},
+        {"no-jit",no_argument,nullptr,1004},
         {nullptr,0,nullptr,0}
     };
     if (argc < 2)
@@ -132,6 +137,8 @@ int main(int argc, char **argv)
         case 1000: arg_seed = strtoull(optarg,nullptr,0); have_seed = true; break;
         case 1001: arg_gpus = atoi(optarg); break;
         case 1002: arg_elem = 4; break;
+        case 1003: arg_jit = 2; break;
+        case 1004: arg_jit = 1; break;
         default: usage(); return 1;
         }
     }
@@ -204,7 +211,18 @@ int main(int argc, char **argv)
     }
     const ffr_flame_desc *desc = ffr_flame_get_desc(flame);
 
-    ffr_ctx *ctx = ffr_cuda_create(desc,nullptr,arg_gpus,err,sizeof(err));
+    ffr_options opt;
+    memset(&opt,0,sizeof(opt));
+    opt.struct_size = sizeof(opt);
+    opt.jit = arg_jit;
+    ffr_ctx *ctx = ffr_cuda_create_ex(desc,nullptr,arg_gpus,&opt,err,sizeof(err));
+    if (!ctx && arg_jit == 2)
+    {
+        /* the flame-specialised kernel is an optimisation: fall back to the interpreter kernels */
+        std::cerr << "note: " << err << "; using the ahead-of-time kernels" << std::endl;
+        opt.jit = 1;
+        ctx = ffr_cuda_create_ex(desc,nullptr,arg_gpus,&opt,err,sizeof(err));
+    }
     if (!ctx)
     {
         std::cerr << "ERROR: " << err << std::endl;

@@ -44,6 +44,25 @@ def test_two_devices_equal_one(ffr, po, examples, name, size):
         np.testing.assert_allclose(col1, col2, rtol=1e-12, atol=1e-9)
 
 
+def test_two_devices_jit_kernel(ffr, examples):
+    """The run-time compiled kernel on a two-device context: one module per device, chains handed
+    out per device by the kernel's own counter, peer-memory reduce: counts equal one device."""
+    if _ndev(ffr) < 2:
+        pytest.skip("needs 2 GPUs")
+    fl = ffr.Flame(examples.example_json("csci6360_project", size=[160, 90]))
+    _, _, cells, cs = fl.layout()
+    bufs = []
+    for devs, jit in (([0], ffr.JIT_OFF), ([0, 1], ffr.JIT_ON)):
+        r = ffr.BufferRenderer(fl, devices=devs, jit=jit)
+        assert r.render(3_000_000, 1000, base_seed=8)
+        assert bool(r.jit_info["active"]) == (jit == ffr.JIT_ON)
+        bufs.append((r.read_buffer(), r.stats))
+        r.close()
+    assert np.array_equal(bufs[0][0], bufs[1][0])
+    for k in ("s_iter", "s_plot", "xf_dist", "pt_min", "pt_max"):
+        assert bufs[0][1][k] == bufs[1][1][k]
+
+
 def test_add_buffer_resume(ffr, po, examples):
     """-i semantics (buffer_renderer.hpp:375-452): counts add as integers, colours as floats."""
     fl = ffr.Flame(examples.example_json("tkoz_test3", size=[96, 54]))
@@ -102,6 +121,35 @@ def test_ffr_buf_cli_roundtrip(ffr, po, examples, tmp_path):
     assert p.returncode == 0, p.stderr
     assert "(not rendering)" in p.stderr
     assert np.array_equal(np.fromfile(out2, dtype=np.uint64), 2 * a)
+
+
+def test_ffr_buf_cli_jit_flag(ffr, examples, tmp_path):
+    """--jit / --no-jit give byte-identical buffer files (same chains, same arithmetic)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(ffr.LIB_PATH), "ffr-buf.out")
+    flame = tmp_path / "csci.json"
+    flame.write_text(examples.example_json("csci6360_project", size=[192, 108]))
+    outs = []
+    for flag in ("--jit", "--no-jit"):
+        out = tmp_path / (flag.strip("-") + ".buf")
+        p = subprocess.run([exe, "-f", str(flame), "-o", str(out), "-s", "2000000", "-b", "1000",
+                            "--seed", "9", flag], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        outs.append(np.fromfile(out, dtype=np.uint64))
+    assert outs[0].sum() > 0 and np.array_equal(outs[0], outs[1])
+
+
+def test_atomic_replay_with_jit_kernel(ffr, examples):
+    """The attractor replay records its trace through whichever render kernel is active."""
+    fl = ffr.Flame(examples.example_json("csci6360_project", size=[256, 256]))
+    r = ffr.BufferRenderer(fl, jit=ffr.JIT_ON)
+    r.render_chains(0, 512, 256, base_seed=1)
+    before = r.fetch_stats()
+    ms1, n1 = r.atomic_roofline(1 << 22, pattern=1)
+    assert ms1 > 0 and 0 < n1 <= (1 << 22) + r.resident_chains
+    assert r.fetch_stats() == before
+    r.close()
 
 
 def test_atomic_roofline_patterns(ffr, examples):
