@@ -565,6 +565,43 @@ bool jit_prepare(ffr_ctx *ctx)
     jit::Config &cfg = ctx->jit_cfg;
     const bool uses_rng = ctx->elem == 8 ? ((const DevFlameT<double>*)ctx->blob.data())->uses_rng != 0
                                          : ((const DevFlameT<float>*)ctx->blob.data())->uses_rng != 0;
+    u64 m0[16];
+    unsigned int m0_32[16];
+    isaac_m0(m0);
+    isaac_m0_32(m0_32);
+    /* K1e: pure-affine flames get the kernel written for them (ffr_jit_affine.cuh) */
+    if (ctx->affine_only && env_int("FFR_JIT_AFFINE",1) != 0)
+    {
+        cfg.affine = true;
+        cfg.async = false;
+        cfg.tpb = env_int("FFR_JIT_TPB",256);
+        cfg.minb = env_int("FFR_JIT_MINB",3);
+        cfg.inline_math = false;
+        cfg.ns = cfg.tpb;
+        cfg.cap = cfg.tpb;
+        std::string why;
+        if (cfg.tpb >= 32 && cfg.tpb <= 1024 && cfg.tpb % 32 == 0)
+            ctx->jit_source = ctx->elem == 8 ? jit::generate_affine<double>(ctx->blob,m0,m0_32,cfg,&cfg.npair,why)
+                                             : jit::generate_affine<float>(ctx->blob,m0,m0_32,cfg,&cfg.npair,why);
+        if (!ctx->jit_source.empty())
+        {
+            /* randmem + randrsl columns, then the coefficient table [pair][xform] */
+            ctx->jit_smem = (size_t)32*cfg.tpb*ctx->elem + (size_t)cfg.npair*ctx->num_xforms*2*ctx->elem;
+            long spills = 0;
+            double secs = 0.0;
+            if (!jit::compile(ctx->jit_source,ctx->jit_cubin,ctx->jit_err,&secs,&ctx->jit_cached,&spills))
+            {
+                ctx->jit_cubin.clear();
+                return false;
+            }
+            ctx->jit_compile_s += secs;
+            ctx->jit_note += "K1e pure-affine kernel, " + std::to_string(cfg.npair) + " table rows, tpb " +
+                std::to_string(cfg.tpb) + ": " + std::to_string(spills) + " spill bytes; ";
+            return true;
+        }
+        cfg.affine = false;
+        ctx->jit_note += why + "; ";
+    }
     cfg.async = env_int("FFR_JIT_ASYNC",1) != 0;
     cfg.tpb = env_int("FFR_JIT_TPB",cfg.async ? 320 : 256);
     cfg.minb = env_int("FFR_JIT_MINB",2);
@@ -603,10 +640,6 @@ bool jit_prepare(ffr_ctx *ctx)
     cfg.ns = ns;
     cfg.cap = pow2ceil(ns);
     ctx->jit_smem = smem_for(ns);
-    u64 m0[16];
-    unsigned int m0_32[16];
-    isaac_m0(m0);
-    isaac_m0_32(m0_32);
     for (int attempt = 0; attempt < 2; ++attempt)
     {
         ctx->jit_source = ctx->elem == 8 ? jit::generate<double>(ctx->blob,ctx->colors,m0,m0_32,cfg)
@@ -644,6 +677,12 @@ int jit_activate(ffr_ctx *ctx)
         ctx->jit_failed = true;
         return FFR_E_UNSUPPORTED;
     }
+    if (ctx->affine_only && !ctx->jit_cfg.affine && ctx->jit_mode == 0)
+    {
+        ctx->jit_failed = true;      /* auto mode: K1e does not cover this flame, K1 stays */
+        ctx->jit_cubin.clear();
+        return FFR_E_UNSUPPORTED;
+    }
     for (DeviceState &ds : ctx->devs)
     {
         CK(cudaSetDevice(ds.dev));
@@ -676,8 +715,9 @@ void jit_maybe(ffr_ctx *ctx, u64 samples)
     if (ctx->jit_ready || ctx->jit_failed || !ctx->jit_eligible || ctx->jit_mode != 0)
         return;
     const char *e = getenv("FFR_JIT_MIN_SAMPLES");
-    /* ~2 s of NVRTC against ~4e-11 s saved per sample over the interpreter kernels */
-    const double min_samples = (e && *e) ? atof(e) : 5e10;
+    /* ~2 s of NVRTC against ~4e-11 s saved per sample over the interpreter kernels (variation
+       flames); ~1 s against ~2e-12 s per sample for pure-affine flames (K1e over K1) */
+    const double min_samples = (e && *e) ? atof(e) : (ctx->affine_only ? 1e12 : 5e10);
     if ((double)samples >= min_samples)
         jit_activate(ctx);
 }
@@ -709,7 +749,7 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
         ctx->err = "chain length (batch size) must be below 2^31 on the device path";
         return FFR_E_INVALID;
     }
-    if (ctx->jit_ready && ctx->jit_cfg.async && chain_count > (1ULL << 30))
+    if (ctx->jit_ready && (ctx->jit_cfg.async || ctx->jit_cfg.affine) && chain_count > (1ULL << 30))
     {
         /* K1d hands out chains through a 32-bit counter: split very long launches */
         const u64 half = 1ULL << 30;
@@ -718,7 +758,7 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
             return rc;
         return launch_render(ctx,ds,chain_first + half,chain_count - half,chain_len,last_len,base_seed,bv_limit);
     }
-    const u64 group_chains = ctx->jit_ready ? (u64)ctx->jit_cfg.ns : (u64)FFR_TPB;
+    const u64 group_chains = ctx->jit_ready ? (ctx->jit_cfg.affine ? 32u : (u64)ctx->jit_cfg.ns) : (u64)FFR_TPB;
     const u64 groups = (chain_count + group_chains - 1) / group_chains;
     if (groups > 0xfffffff0ULL)
     {
@@ -734,7 +774,9 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
         prm.rsl_scratch = ds.d_rsl_jit;
         void *args[] = {&prm};
         jit::Api &a = jit::api(true);
-        const CUresult r = a.LaunchKernel(ds.jmod.fn,(unsigned)grid,1,1,(unsigned)ctx->jit_cfg.tpb,1,1,
+        /* K1e: scatter diagnostics (warp aggregation, discard, trace) live in a second entry point */
+        CUfunction fn = (ctx->scatter_mode != FFR_SCATTER_GLOBAL && ds.jmod.fn_modes) ? ds.jmod.fn_modes : ds.jmod.fn;
+        const CUresult r = a.LaunchKernel(fn,(unsigned)grid,1,1,(unsigned)ctx->jit_cfg.tpb,1,1,
             (unsigned)ctx->jit_smem,(CUstream)ds.stream,args,nullptr);
         if (r != CUDA_SUCCESS)
         {
@@ -918,7 +960,10 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
         if (e && *e == '0') ctx->jit_mode = 1;
         else if (e && *e == '1') ctx->jit_mode = 2;
     }
-    ctx->jit_eligible = ctx->jit_mode != 1 && jit_supported(ctx) && (ctx->jit_mode == 2 || !ctx->affine_only);
+    /* pure-affine flames: K1e where it applies (r = 0, no final xform, ...); in auto mode the
+       queue-scheduled kernel is not tried for them, K1 is the better kernel there */
+    ctx->jit_eligible = ctx->jit_mode != 1 && jit_supported(ctx) &&
+        (ctx->jit_mode == 2 || !ctx->affine_only || (ctx->r == 0 && !ctx->has_final));
     if (ctx->jit_mode == 2 && ctx->opt.jit == 2)
     {
         if (!ctx->jit_eligible)

@@ -42,6 +42,8 @@ struct Config
     int minb = 2;           /* blocks per SM asked of ptxas (register cap) */
     bool inline_math = false;
     bool async = true;      /* K1d (ffr_jit_async.cuh, queue scheduled) instead of K1c (lock step) */
+    bool affine = false;    /* K1e (ffr_jit_affine.cuh): pure-affine flame, one chain per thread */
+    int npair = 0;          /* K1e: 16-byte rows of the per-xform coefficient table */
 };
 
 struct Api
@@ -382,6 +384,351 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
     return h.str() + o.str();
 }
 
+/* ---- K1e: pure-affine flames (ffr_jit_affine.cuh) ----
+
+   The xform of a pure-affine flame is (types/xform.hpp:211-227, types/affine.hpp:104-110,
+   types/point.hpp:215-225), per output coordinate i:
+       t[i]   = b_pre[i]  + (((0 + A_pre[i][0]*p[0]) + A_pre[i][1]*p[1]) [+ A_pre[i][2]*p[2]])
+       v[i]   = (0 + t[i]*w_0) [+ t[i]*w_1 ...]          (one term per `linear` variation)
+       out[i] = b_post[i] + (((0 + A_post[i][0]*v[0]) + ...))
+   Every xform runs this same code on its own coefficients, so the generated function takes a
+   coefficient either from the constant bank (identical for all xforms) or from a per-xform
+   table in shared memory (it differs). Coefficients known at compile time allow steps to be
+   dropped -- but only where the result is PROVABLY the same IEEE number, sign of zero included
+   (there is no -ffast-math anywhere). With every intermediate finite (checked below from the
+   coefficient magnitudes) the rules are:
+     R1  x*1 == x,  x*(-1) == -x   exactly, zeros included.
+     R2  a*x with a == +-0 is +-0, and z + (+-0) == z for z != 0: a zero term changes at most
+         the SIGN OF A ZERO partial sum, never a nonzero value. The same holds for the leading
+         `0 +`.
+     R3  b + S, with b not -0.0: equals b for S == +0 and for S == -0 alike (b != 0: exact;
+         b == +0: +0 + (+-0) == +0). So a row whose offset b is never -0.0 ("absorbing") yields
+         the reference's bits from ANY S that equals the reference's S as a real number: zero
+         terms and the leading 0 are dropped (R2). Its result is never -0.0.
+     R4  +0 + S == S when S is never -0.0; a sum is never -0.0 if one operand never is.
+   A row whose offset is -0.0 for some xform is emitted in the reference's full form. The sum v
+   may drop its leading `0 +` only if every consumer is an absorbing row; otherwise it keeps it
+   (or is t itself: one variation of weight 1 and t never -0.0).
+   Returns "" and sets `why` if the flame is outside what K1e covers; the caller then keeps the
+   interpreter kernel. */
+template <typename T> struct AfCoef
+{
+    bool uniform = true;      /* identical bits for every xform */
+    T value = 0;              /* if uniform */
+    bool any_negzero = false; /* some xform holds -0.0 here */
+    std::string ref;          /* how the generated code reads it */
+};
+
+struct AfVal { std::string e; bool nz; };   /* expression, "never -0.0" */
+
+template <typename T>
+AfVal af_row(const AfCoef<T> &b, const std::vector<AfCoef<T>> &a, const std::vector<AfVal> &x)
+{
+    const size_t D = x.size();
+    if (b.any_negzero)
+    {
+        /* the reference's expression in full */
+        std::string s = "(T)0.0";
+        for (size_t j = 0; j < D; ++j)
+            s = "(" + s + " + " + a[j].ref + "*" + x[j].e + ")";
+        return {"(" + b.ref + " + " + s + ")",false};
+    }
+    std::string s;
+    bool snz = false;
+    for (size_t j = 0; j < D; ++j)
+    {
+        std::string term;
+        bool tnz = false;
+        if (a[j].uniform && a[j].value == (T)0)
+            continue;                                          /* R2 */
+        if (a[j].uniform && a[j].value == (T)1)
+        {
+            term = x[j].e;                                     /* R1 */
+            tnz = x[j].nz;
+        }
+        else if (a[j].uniform && a[j].value == (T)-1)
+            term = "(-" + x[j].e + ")";                        /* R1 */
+        else
+            term = "(" + a[j].ref + "*" + x[j].e + ")";
+        if (s.empty())
+        {
+            s = term;
+            snz = tnz;
+        }
+        else
+        {
+            s = "(" + s + " + " + term + ")";
+            snz = snz || tnz;
+        }
+    }
+    if (s.empty())
+        return {b.ref,true};                                   /* b + (+0) */
+    if (b.uniform && b.value == (T)0)
+        return {snz ? s : "((T)0.0 + " + s + ")",true};         /* R4 */
+    return {"(" + b.ref + " + " + s + ")",true};                /* R3 */
+}
+
+template <typename T>
+std::string generate_affine(const std::vector<unsigned char> &blobv, const u64 *m0, const unsigned int *m0_32,
+        const Config &cfg, int *npair_out, std::string &why)
+{
+    const unsigned char *blob = blobv.data();
+    const DevFlameT<T> *fl = (const DevFlameT<T>*)blob;
+    const DevXFormT<T> *xfs = (const DevXFormT<T>*)(blob + fl->xf_off);
+    const DevVarT<T> *vars = (const DevVarT<T>*)(blob + fl->var_off);
+    const int D = (int)fl->dims, NX = (int)fl->num_xforms;
+    auto no = [&](const char *m) { why = std::string("K1e: ") + m; return std::string(); };
+    if (fl->r != 0 || fl->has_final)
+        return no("colour dimensions or a final xform");
+    if (NX < 1 || NX > 8)
+        return no("more than 8 xforms");
+    const uint32_t nvar = xfs[0].var_count;
+    const uint32_t pre = D < 3 ? 1u : (xfs[0].flags & XF_HAS_PRE), post = D < 3 ? 1u : (xfs[0].flags & XF_HAS_POST);
+    if (nvar < 1 || nvar > 4)
+        return no("0 or more than 4 variations per xform");
+    double row_pre = 1.0, row_post = 1.0, b_pre = 0.0, b_post = 0.0, wsum = 0.0;
+    for (int k = 0; k < NX; ++k)
+    {
+        const DevXFormT<T> &xf = xfs[k];
+        if (xf.var_count != nvar || (D == 3 && ((xf.flags & XF_HAS_PRE) != pre || (xf.flags & XF_HAS_POST) != post)))
+            return no("xforms of different shape");
+        double ws = 0.0;
+        for (uint32_t q = 0; q < nvar; ++q)
+        {
+            if (vars[xf.var_begin + q].op != FFR_VAR_LINEAR)
+                return no("a variation other than linear");
+            ws += std::fabs((double)vars[xf.var_begin + q].weight);
+        }
+        wsum = std::max(wsum,ws);
+        for (int i = 0; i < D; ++i)
+        {
+            double rp = 0.0, rq = 0.0;
+            for (int j = 0; j < D; ++j)
+            {
+                rp += std::fabs((double)xf.pre_A[i*D + j]);
+                rq += std::fabs((double)xf.post_A[i*D + j]);
+            }
+            if (pre) { row_pre = std::max(row_pre,rp); b_pre = std::max(b_pre,std::fabs((double)xf.pre_b[i])); }
+            if (post) { row_post = std::max(row_post,rq); b_post = std::max(b_post,std::fabs((double)xf.post_b[i])); }
+        }
+    }
+    /* every intermediate stays finite: |out| <= alpha*|p| + beta per application, |p| <= 1 at the
+       start of a chain, and the settle iterations run unchecked (render_iterator.hpp:55-57) */
+    const double alpha = row_pre*wsum*row_post, beta = b_pre*wsum*row_post + b_post;
+    const int settle = sizeof(T) == 8 ? 53 : 24;
+    const double thr = sizeof(T) == 8 ? 1e20 : 1e10, room = sizeof(T) == 8 ? 290.0 : 34.0;
+    if (!(std::isfinite(alpha) && std::isfinite(beta)) ||
+            std::log10(std::max(alpha,1.0))*(settle + 2) + std::log10(1.0 + beta) + std::log10(thr)*0.0 + 4.0 > room ||
+            std::log10(std::max(alpha,1.0)) + std::log10(thr) + std::log10(1.0 + beta) + 4.0 > room)
+        return no("coefficients too large to prove every intermediate finite");
+    u64 cells = 1;
+    bool idx32 = true;
+    for (int i = 0; i < D; ++i)
+    {
+        /* in bounds => not a bad value (the kernel tests bad values only for unplotted samples) */
+        if (!(std::fabs((double)fl->lo[i]) <= thr && std::fabs((double)fl->hi[i]) <= thr))
+            return no("bounds beyond the bad value threshold");
+        const u64 size_i = (i + 1 < D) ? fl->mult_i[i + 1]/fl->mult_i[i] : fl->cells/fl->mult_i[i];
+        if (size_i >= (1ULL << 31))
+            idx32 = false;
+        cells *= size_i;
+    }
+    if (fl->cells >= (1ULL << 32))
+        idx32 = false;
+
+    /* classify every coefficient position over the xforms */
+    Pool<T> pool;
+    std::vector<T> table;   /* varying coefficients: [position][xform] */
+    auto classify = [&](auto get) {
+        AfCoef<T> c;
+        c.value = get(0);
+        for (int k = 0; k < NX; ++k)
+        {
+            const T v = get(k);
+            if (memcmp(&v,&c.value,sizeof(T)) != 0)
+                c.uniform = false;
+            if (v == (T)0 && std::signbit(v))
+                c.any_negzero = true;
+        }
+        if (c.uniform)
+            c.ref = pool.ref(c.value);
+        else
+        {
+            const size_t pos = table.size()/NX;
+            for (int k = 0; k < NX; ++k)
+                table.push_back(get(k));
+            c.ref = "q" + std::to_string(pos/2) + (pos % 2 ? ".y" : ".x");
+        }
+        return c;
+    };
+    std::vector<std::vector<AfCoef<T>>> Apre(D), Apost(D);
+    std::vector<AfCoef<T>> bpre(D), bpost(D), w(nvar);
+    for (int i = 0; i < D; ++i)
+    {
+        if (pre)
+        {
+            for (int j = 0; j < D; ++j)
+                Apre[i].push_back(classify([&](int k) { return xfs[k].pre_A[i*D + j]; }));
+            bpre[i] = classify([&](int k) { return xfs[k].pre_b[i]; });
+        }
+    }
+    for (uint32_t q = 0; q < nvar; ++q)
+        w[q] = classify([&](int k) { return vars[xfs[k].var_begin + q].weight; });
+    bool post_absorbing = post != 0;
+    for (int i = 0; i < D; ++i)
+    {
+        if (post)
+        {
+            for (int j = 0; j < D; ++j)
+                Apost[i].push_back(classify([&](int k) { return xfs[k].post_A[i*D + j]; }));
+            bpost[i] = classify([&](int k) { return xfs[k].post_b[i]; });
+            if (bpost[i].any_negzero)
+                post_absorbing = false;
+        }
+    }
+    if (table.size()/NX % 2)
+        for (int k = 0; k < NX; ++k)
+            table.push_back((T)0);
+    const int npair = (int)(table.size()/NX/2);
+    if (npair_out) *npair_out = npair;
+
+    /* the expressions; p is never -0.0 (2u-1 is not, and neither is any `out` below) unless a
+       non-absorbing row produces it, in which case nothing is assumed about p */
+    std::vector<AfVal> out;
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        const bool p_nz = pass == 0;
+        std::vector<AfVal> x(D), t(D), v(D);
+        for (int i = 0; i < D; ++i)
+            x[i] = {"x" + std::to_string(i),p_nz};
+        for (int i = 0; i < D; ++i)
+            t[i] = pre ? af_row<T>(bpre[i],Apre[i],x) : x[i];
+        /* name the rows so that each is evaluated once */
+        std::vector<AfVal> tn(D);
+        for (int i = 0; i < D; ++i)
+            tn[i] = {"t" + std::to_string(i),t[i].nz};
+        for (int i = 0; i < D; ++i)
+        {
+            std::string s;
+            bool snz = false;
+            for (uint32_t q = 0; q < nvar; ++q)
+            {
+                std::string term;
+                bool tnz = false;
+                if (w[q].uniform && w[q].value == (T)1) { term = tn[i].e; tnz = tn[i].nz; }   /* R1 */
+                else if (w[q].uniform && w[q].value == (T)-1) term = "(-" + tn[i].e + ")";
+                else term = "(" + tn[i].e + "*" + w[q].ref + ")";
+                if (s.empty()) { s = term; snz = tnz; }
+                else { s = "(" + s + " + " + term + ")"; snz = snz || tnz; }
+            }
+            if (snz || post_absorbing)
+                v[i] = {s,snz};                       /* R4 / consumers are absorbing rows (R3) */
+            else
+                v[i] = {"((T)0.0 + " + s + ")",true};
+        }
+        std::vector<AfVal> vn(D);
+        for (int i = 0; i < D; ++i)
+            vn[i] = {"v" + std::to_string(i),v[i].nz};
+        out.assign(D,AfVal());
+        bool all_nz = true;
+        for (int i = 0; i < D; ++i)
+        {
+            out[i] = post ? af_row<T>(bpost[i],Apost[i],vn) : vn[i];
+            all_nz = all_nz && out[i].nz;
+        }
+        if (pass == 0 && !all_nz)
+            continue;        /* p may be -0.0: redo without that assumption */
+        std::ostringstream h, o;
+        h << "/* generated by libffr_cuda for one pure-affine flame (ffr_jit_host.cuh); kernel: ffr_jit_affine.cuh */\n";
+        h << "#define FFR_TPB " << cfg.tpb << "\n";
+        h << "#define FFR_ISAAC_M0_INIT {";
+        for (int i = 0; i < 16; ++i)
+            h << (i ? "," : "") << m0[i] << "ULL";
+        h << "}\n#define FFR_ISAAC_M0_32_INIT {";
+        for (int i = 0; i < 16; ++i)
+            h << (i ? "," : "") << m0_32[i] << "u";
+        h << "}\n#include \"ffr_params.cuh\"\n";
+        h << "typedef " << (sizeof(T) == 8 ? "double" : "float") << " JT;\n";
+        h << "typedef " << (sizeof(T) == 8 ? "double2" : "float2") << " JPAIR;\n";
+        h << "typedef " << (idx32 ? "unsigned int" : "unsigned long long") << " JIDX;\n";
+        h << "#define JD " << D << "\n#define JR 0\n#define JNX " << NX << "\n#define JNS " << cfg.tpb
+          << "\n#define JTPB " << cfg.tpb << "\n#define JMINB " << cfg.minb << "\n#define JNPAIR " << npair << "\n\n";
+        o << "/* XForm::applyIteration for every xform of the flame; tb = coefficient table + xform index */\n";
+        if (p_nz)
+            o << "/* relies on: no coordinate of pin is -0.0 (true for 2u-1 and for every pout of this function) */\n";
+        o << "__device__ __forceinline__ void jaf_xform(const JPAIR *tb, const JT *pin, JT *pout)\n{\n    typedef JT T;\n";
+        for (int r = 0; r < npair; ++r)
+            o << "    const JPAIR q" << r << " = tb[" << r << "*JNX];\n";
+        for (int i = 0; i < D; ++i)
+            o << "    const T x" << i << " = pin[" << i << "];\n";
+        for (int i = 0; i < D; ++i)
+            o << "    const T t" << i << " = " << t[i].e << ";\n";
+        for (int i = 0; i < D; ++i)
+            o << "    const T v" << i << " = " << v[i].e << ";\n";
+        for (int i = 0; i < D; ++i)
+            o << "    pout[" << i << "] = " << out[i].e << ";\n";
+        o << "}\n\n";
+        /* Flame::getRandomXForm (types/flame.hpp:212-219), as in generate() */
+        o << "__device__ __forceinline__ unsigned jit_select(JT r)\n{\n    unsigned i = 0;\n";
+        for (int k = 0; k + 1 < NX; ++k)
+            o << "    i += (" << pool.ref(fl->xfcw[k]) << " < r) ? 1u : 0u;\n";
+        o << "    return i;\n}\n\n";
+        /* on the raw word: xfcw[k] < (w >> s)/2^b  <=>  (w >> s) > floor(xfcw[k]*2^b)  <=>
+           w > (floor(xfcw[k]*2^b) << s | (2^s - 1)) */
+        o << "__device__ __forceinline__ unsigned jit_select_word(Real<JT>::word w)\n{\n    unsigned i = 0;\n";
+        for (int k = 0; k + 1 < NX; ++k)
+        {
+            const int bbits = sizeof(T) == 8 ? 53 : 24, sbits = sizeof(T) == 8 ? 11 : 8;
+            const double scaled = std::floor(std::ldexp((double)fl->xfcw[k],bbits));
+            if (fl->xfcw[k] < (T)0)
+                o << "    i += 1u;\n";
+            else if (scaled >= std::ldexp(1.0,bbits))
+                o << "    /* table entry >= 1: never below r */\n";
+            else
+            {
+                const unsigned long long m = (unsigned long long)scaled;
+                const unsigned long long thrw = (m << sbits) | ((1ULL << sbits) - 1ULL);
+                o << "    i += (w > (Real<JT>::word)" << thrw << "ULL) ? 1u : 0u;\n";
+            }
+        }
+        o << "    return i;\n}\n\n";
+        o << "__device__ __forceinline__ bool jit_inb(const JT *pf)\n{\n    bool inb = true;\n";
+        for (int i = 0; i < D; ++i)
+            o << "    inb &= (pf[" << i << "] >= " << pool.ref(fl->lo[i]) << ") & (pf[" << i << "] <= " << pool.ref(fl->hi[i]) << ");\n";
+        o << "    return inb;\n}\n\n";
+        /* buffer_renderer.hpp:202-209; sizes < 2^31 and cells < 2^32: the truncating conversion
+           and the index arithmetic fit 32 bits (same values) */
+        const char *cvt = idx32 ? (sizeof(T) == 8 ? "__double2uint_rz" : "__float2uint_rz") : "to_index";
+        o << "__device__ __forceinline__ JIDX jaf_index(const JT *pf)\n{\n";
+        o << "    JIDX bi = " << cvt << "((pf[0] - " << pool.ref(fl->lo[0]) << ") * " << pool.ref(fl->mult_d[0]) << ");\n";
+        for (int i = 1; i < D; ++i)
+            o << "    bi += (JIDX)" << cvt << "((pf[" << i << "] - " << pool.ref(fl->lo[i]) << ") * " << pool.ref(fl->mult_d[i]) << ") * (JIDX)"
+              << fl->mult_i[i] << "ULL;\n";
+        o << "    return bi;\n}\n\n";
+        o << "__device__ __forceinline__ u64 jit_json_id(unsigned k)\n{\n    switch (k)\n    {\n";
+        for (int k = 0; k < NX; ++k)
+            o << "    case " << k << ": return " << xfs[k].json_id << "ULL;\n";
+        o << "    default: return 0;\n    }\n}\n\n";
+        o << "#include \"ffr_jit_affine.cuh\"\n";
+        h << "__constant__ JT jc[" << (pool.vals.empty() ? 1 : pool.vals.size()) << "] = {";
+        for (size_t i = 0; i < pool.vals.size(); ++i)
+            h << (i ? "," : "") << lit(pool.vals[i]);
+        if (pool.vals.empty())
+            h << "0";
+        h << "};\n";
+        h << "__constant__ JT jtab[" << (table.empty() ? 2 : table.size()) << "] = {";
+        /* [pair][xform][2] */
+        if (table.empty())
+            h << "0,0";
+        for (int r = 0; r < npair; ++r)
+            for (int k = 0; k < NX; ++k)
+                h << ((r || k) ? "," : "") << lit(table[(size_t)(2*r)*NX + k]) << "," << lit(table[(size_t)(2*r + 1)*NX + k]);
+        h << "};\n\n";
+        return h.str() + o.str();
+    }
+    return no("internal");
+}
+
 /* ---- compile + cache ---- */
 
 inline u64 fnv1a(const void *data, size_t n, u64 h = 0xcbf29ce484222325ULL)
@@ -425,6 +772,7 @@ inline const std::vector<Shim> &headers()
         {"ffr_params.cuh",(const char*)ffr_embed_params,ffr_embed_params_len},
         {"ffr_jit_kernel.cuh",(const char*)ffr_embed_jit_kernel,ffr_embed_jit_kernel_len},
         {"ffr_jit_async.cuh",(const char*)ffr_embed_jit_async,ffr_embed_jit_async_len},
+        {"ffr_jit_affine.cuh",(const char*)ffr_embed_jit_affine,ffr_embed_jit_affine_len},
         {"../../include/ffr_cuda.h",(const char*)ffr_embed_abi,ffr_embed_abi_len},
         {"cstdint",shim_int,sizeof(shim_int)-1},
         {"stdint.h",shim_int,sizeof(shim_int)-1},
@@ -612,6 +960,7 @@ struct Module
 {
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;
+    CUfunction fn_modes = nullptr;   /* K1e: the variant that honours prm.scatter_mode */
     int regs = 0;
 };
 
@@ -649,6 +998,10 @@ inline bool load(const std::vector<char> &cubin, size_t smem, Module &m, std::st
         return false;
     }
     a.FuncGetAttribute(&m.regs,CU_FUNC_ATTRIBUTE_NUM_REGS,m.fn);
+    if (a.ModuleGetFunction(&m.fn_modes,m.mod,"ffr_jit_render_modes") != CUDA_SUCCESS)
+        m.fn_modes = nullptr;
+    else if (a.FuncSetAttribute(m.fn_modes,CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,(int)smem) != CUDA_SUCCESS)
+        m.fn_modes = nullptr;
     return true;
 }
 

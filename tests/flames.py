@@ -270,3 +270,56 @@ def multi_variation_flame(names, dims=2, size=None, color=True, final_name=None)
             fl["final_xform"]["color"] = [0.5, 0.5]
             fl["final_xform"]["color_speed"] = 0.25
     return json.dumps(fl, indent=1)
+
+
+def affine_flame(dims=2, nx=3, pre="general", post="identity", weights=(1.0,), size=None,
+                 bounds=None, neg_zero=None, vary_weights=False):
+    """Pure-affine flames for the flame-specialised affine kernel (K1e) and its exact
+    simplifier (csrc/ffr_jit_host.cuh): every combination of coefficient shapes the generator
+    treats differently -- coefficients identical across xforms or not, 0 / +1 / -1 entries,
+    offsets that are +0, -0.0 or vary, one or several `linear` variations, present / absent
+    pre and post affines (3-d only: absent means skipped, reference xform.hpp:216,222).
+      pre / post: "general" (all entries differ per xform), "scale" (0.5*I, offsets differ),
+                  "identity", "perm" (a signed permutation: entries 0, +1, -1), "none" (omit)
+      neg_zero:   ("pre"|"post", row, xform) puts -0.0 into that offset
+    """
+    if size is None:
+        size = {1: [4096], 2: [160, 120], 3: [40, 36, 32]}[dims]
+    if bounds is None:
+        bounds = [[-1.5, 1.5]] * dims
+
+    def mat(kind, k):
+        if kind == "general":
+            A = [[(0.45 if i == j else 0.0) + 0.07 * ((i * 3 + j * 5 + k * 2) % 5 - 2) for j in range(dims)]
+                 for i in range(dims)]
+            b = [0.5 * (((k * 7 + i * 3) % 9) / 4.0 - 1.0) for i in range(dims)]
+        elif kind == "scale":
+            A = [[0.5 if i == j else 0.0 for j in range(dims)] for i in range(dims)]
+            b = [0.5 * ((k >> i) & 1) - (0.25 if i == 0 else 0.0) for i in range(dims)]
+        elif kind == "identity":
+            A = [[1.0 if i == j else 0.0 for j in range(dims)] for i in range(dims)]
+            b = [0.0] * dims
+        elif kind == "perm":
+            A = [[0.0] * dims for _ in range(dims)]
+            for i in range(dims):
+                A[i][(i + 1) % dims] = -1.0 if i == 0 else 1.0
+            b = [0.0] * dims
+        else:
+            raise ValueError(kind)
+        return A, b
+
+    xfs = []
+    for k in range(nx):
+        ws = [w * (1.0 + 0.1 * k) if vary_weights else w for w in weights]
+        xf = {"weight": 1.0 + 0.25 * (k % 3),
+              "variations": [{"name": "linear", "weight": w} for w in ws]}
+        for which, kind in (("pre", pre), ("post", post)):
+            if kind == "none":
+                continue
+            A, b = mat(kind, k)
+            if neg_zero is not None and neg_zero[0] == which and neg_zero[2] == k:
+                b[neg_zero[1]] = -0.0
+            xf[which + "_affine"] = {"A": A, "b": b}
+        xfs.append(xf)
+    fl = {"dimensions": dims, "size": size, "bounds": bounds, "xforms": xfs}
+    return json.dumps(fl, indent=1)
