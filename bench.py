@@ -230,7 +230,7 @@ def main():
     # outside every timed region, like the ahead-of-time build of the interpreter kernels
     jit = args.jit
     if jit < 0:
-        jit = ffr.JIT_OFF if flame.uses_only([1]) else ffr.JIT_ON   # op 1 = linear
+        jit = ffr.JIT_ON   # flame-specialised kernels: K1d (variations), K1e (pure-affine flames)
     t_create = time.perf_counter()
     rend = ffr.BufferRenderer(flame, devices=[local_rank], external_buffer=buf.data_ptr(),
                               stream=stream.cuda_stream, scatter_mode=args.scatter, jit=jit)

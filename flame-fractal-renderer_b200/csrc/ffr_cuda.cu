@@ -141,6 +141,7 @@ struct DeviceState
     jit::Module jmod;              /* K1c: the flame-specialised kernel loaded on this device */
     int jit_blocks_per_sm = 0;
     void *d_rsl_jit = nullptr;     /* K1c randrsl scratch */
+    void *d_acc = nullptr;         /* K1e accumulation tile (scrambled cell order), cells words */
 };
 
 typedef void (*render_fn)(const RenderParams);
@@ -579,6 +580,28 @@ bool jit_prepare(ffr_ctx *ctx)
         cfg.inline_math = false;
         cfg.ns = cfg.tpb;
         cfg.cap = cfg.tpb;
+        /* Accumulation tile in scrambled cell order (fold_acc_kernel) for power-of-two cell counts.
+           Measured on B200 (samples/s, linear -> scrambled): sierpinski@1024^2 (8 MiB) 1.40e11 ->
+           2.04e11, barnsley@2048^2 (32 MiB) 1.57e11 -> 1.88e11 with single cells scrambled; at
+           128 MiB single cells lose for a dense attractor (barnsley@4096^2 1.81e11 -> 1.68e11: every
+           touched cell becomes a sector of its own and the touched sectors no longer fit L2) while
+           scrambling whole 32-byte sectors still wins (1.86e11; sierpinski@4096^2 1.84e11 -> 2.03e11,
+           sierpinski_3d@256^3 1.63e11 -> 1.76e11); at 1 GiB (sierpinski_3d@512^3) every variant loses
+           (8.2e10 -> 5.4e10), so large buffers are scattered into directly. */
+        cfg.acc_mul = 0;
+        cfg.acc_gran = 0;
+        {
+            const u64 bytes = ctx->cells*ctx->elem;
+            const u64 max_bytes = (u64)env_int("FFR_ACC_MAX_MB",128) << 20;
+            if (env_int("FFR_K1E_SCRAMBLE",1) != 0 && ctx->r == 0 && ctx->cells >= 4096 &&
+                    (ctx->cells & (ctx->cells - 1)) == 0 && bytes <= max_bytes && ctx->cells <= (1ULL << 31))
+            {
+                cfg.acc_mul = 0x9E3779B1u;
+                /* cells per 32-byte sector stay together above 32 MiB */
+                const int sector = ctx->elem == 8 ? 2 : 3;
+                cfg.acc_gran = (unsigned)env_int("FFR_ACC_GRAN",bytes <= (32u << 20) ? 0 : sector);
+            }
+        }
         std::string why;
         if (cfg.tpb >= 32 && cfg.tpb <= 1024 && cfg.tpb % 32 == 0)
             ctx->jit_source = ctx->elem == 8 ? jit::generate_affine<double>(ctx->blob,m0,m0_32,cfg,&cfg.npair,why)
@@ -595,7 +618,8 @@ bool jit_prepare(ffr_ctx *ctx)
                 return false;
             }
             ctx->jit_compile_s += secs;
-            ctx->jit_note += "K1e pure-affine kernel, " + std::to_string(cfg.npair) + " table rows, tpb " +
+            ctx->jit_note += std::string("K1e pure-affine kernel, ") + (cfg.acc_mul ? "scrambled accumulation tile, " : "") +
+                std::to_string(cfg.npair) + " table rows, tpb " +
                 std::to_string(cfg.tpb) + ": " + std::to_string(spills) + " spill bytes; ";
             return true;
         }
@@ -704,6 +728,11 @@ int jit_activate(ffr_ctx *ctx)
             nb = (int)ctx->opt.blocks_per_sm;
         ds.jit_blocks_per_sm = nb;
         CK(cudaMalloc(&ds.d_rsl_jit,(size_t)ds.sm_count*nb*16*ctx->jit_cfg.ns*ctx->elem));
+        if (ctx->jit_cfg.affine && ctx->jit_cfg.acc_mul)
+        {
+            CK(cudaMalloc(&ds.d_acc,(size_t)ctx->cells*ctx->elem));
+            CK(cudaMemsetAsync(ds.d_acc,0,(size_t)ctx->cells*ctx->elem,ds.stream));
+        }
     }
     ctx->jit_ready = true;
     return FFR_OK;
@@ -744,6 +773,7 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
     prm.bv_limit = bv_limit;
     prm.blob_bytes = (uint32_t)ctx->blob.size();
     prm.scatter_mode = ctx->scatter_mode;
+    prm.acc = ds.d_acc;
     if (chain_len >= (1ULL << 31) - 64)
     {
         ctx->err = "chain length (batch size) must be below 2^31 on the device path";
@@ -782,6 +812,19 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
         {
             ctx->err = "cuLaunchKernel(ffr_jit_render): " + jit::cu_err(a,r);
             return FFR_E_CUDA;
+        }
+        if (ds.d_acc && fn == ds.jmod.fn)
+        {
+            /* K2b: the launch's scrambled tile into the buffer (reference cell order) */
+            uint32_t inv = ctx->jit_cfg.acc_mul;      /* Newton: x <- x*(2 - m*x) doubles the valid bits */
+            for (int i = 0; i < 5; ++i)
+                inv *= 2u - ctx->jit_cfg.acc_mul*inv;
+            const unsigned fgrid = (unsigned)std::min<u64>((ctx->cells + 255)/256,(u64)ds.sm_count*16);
+            if (ctx->elem == 8)
+                fold_acc_kernel<u64><<<fgrid,256,0,ds.stream>>>((u64*)ds.d_acc,(u64*)ds.buffer,ctx->cells,inv,ctx->jit_cfg.acc_gran);
+            else
+                fold_acc_kernel<unsigned int><<<fgrid,256,0,ds.stream>>>((unsigned int*)ds.d_acc,(unsigned int*)ds.buffer,ctx->cells,inv,ctx->jit_cfg.acc_gran);
+            ++ctx->launches;
         }
     }
     else
@@ -995,6 +1038,7 @@ void ffr_cuda_destroy(ffr_ctx *ctx)
         if (ds.d_scratch) cudaFree(ds.d_scratch);
         if (ds.d_rsl) cudaFree(ds.d_rsl);
         if (ds.d_rsl_jit) cudaFree(ds.d_rsl_jit);
+        if (ds.d_acc) cudaFree(ds.d_acc);
         if (ds.jmod.mod) jit::unload(ds.jmod);
         if (ds.d_stage) cudaFree(ds.d_stage);
         if (ds.own_stream && ds.stream) cudaStreamDestroy(ds.stream);

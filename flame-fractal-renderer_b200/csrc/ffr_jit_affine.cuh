@@ -27,7 +27,10 @@ int -> fp conversion of the selection draw, unconditional min/max selects. Here:
    threshold), so the bad value test runs only for samples that are not plotted;
  * the extremes (buffer_renderer.hpp:188-194) are updated behind one combined, rarely taken
    branch instead of 4*D unconditional compare-and-selects;
- * s_iter follows from the chain lengths; s_plot = s_iter - (samples not plotted).
+ * s_iter follows from the chain lengths; s_plot = s_iter - (samples not plotted);
+ * for L2-resident power-of-two buffers the launch scatters into a tile of its own whose cell
+   order is scrambled (JACC_MUL), folded into the buffer afterwards (fold_acc_kernel): an
+   attractor's cell addresses are strongly patterned and load the L2 slices unevenly.
 
 Everything else is the reference's arithmetic in the reference's order (-fmad=false), so the
 histogram counts and statistics equal K1's bit for bit (tests/test_gpu_jit.py).
@@ -162,6 +165,9 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
 
     W *col = rng_base + tid, *rcol = rsl_base + tid;
     W *__restrict__ buffer = (W*)prm.buffer;
+#ifdef JACC_MUL
+    W *__restrict__ acc = (W*)prm.acc;
+#endif
     const bool warp_agg = MODES && prm.scatter_mode == FFR_SCATTER_WARP_AGG;
     const bool discard = MODES && (prm.scatter_mode == FFR_SCATTER_DISCARD || prm.scatter_mode == FFR_SCATTER_TRACE);
     u64 *__restrict__ trace = (MODES && prm.scatter_mode == FFR_SCATTER_TRACE) ? prm.trace : nullptr;
@@ -308,6 +314,12 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
                     {
                         const JIDX bi = jaf_index(p); /* :202-209 */
                         W *cell = buffer + bi;
+#ifdef JACC_MUL
+                        /* the launch's own tile, cells in scrambled order (fold_acc_kernel) */
+                        if (!MODES)
+                            cell = acc + ((((((unsigned)bi >> JACC_GRAN)*JACC_MUL) & JACC_MASK) << JACC_GRAN) |
+                                          ((unsigned)bi & ((1u << JACC_GRAN) - 1u)));
+#endif
                         if (!MODES)
                             hist_add(cell,1u); /* :211-215 */
                         else

@@ -44,6 +44,8 @@ struct Config
     bool async = true;      /* K1d (ffr_jit_async.cuh, queue scheduled) instead of K1c (lock step) */
     bool affine = false;    /* K1e (ffr_jit_affine.cuh): pure-affine flame, one chain per thread */
     int npair = 0;          /* K1e: 16-byte rows of the per-xform coefficient table */
+    unsigned acc_mul = 0;   /* K1e: scramble multiplier of the accumulation tile (0: scatter into the buffer) */
+    unsigned acc_gran = 0;  /* K1e: log2 of the cells that stay together in the tile */
 };
 
 struct Api
@@ -652,7 +654,11 @@ std::string generate_affine(const std::vector<unsigned char> &blobv, const u64 *
         h << "typedef " << (sizeof(T) == 8 ? "double2" : "float2") << " JPAIR;\n";
         h << "typedef " << (idx32 ? "unsigned int" : "unsigned long long") << " JIDX;\n";
         h << "#define JD " << D << "\n#define JR 0\n#define JNX " << NX << "\n#define JNS " << cfg.tpb
-          << "\n#define JTPB " << cfg.tpb << "\n#define JMINB " << cfg.minb << "\n#define JNPAIR " << npair << "\n\n";
+          << "\n#define JTPB " << cfg.tpb << "\n#define JMINB " << cfg.minb << "\n#define JNPAIR " << npair << "\n";
+        if (cfg.acc_mul)
+            h << "#define JACC_MUL " << cfg.acc_mul << "u\n#define JACC_MASK " << ((fl->cells - 1) >> cfg.acc_gran)
+              << "u\n#define JACC_GRAN " << cfg.acc_gran << "\n";
+        h << "\n";
         o << "/* XForm::applyIteration for every xform of the flame; tb = coefficient table + xform index */\n";
         if (p_nz)
             o << "/* relies on: no coordinate of pin is -0.0 (true for 2u-1 and for every pout of this function) */\n";
@@ -704,6 +710,15 @@ std::string generate_affine(const std::vector<unsigned char> &blobv, const u64 *
         for (int i = 1; i < D; ++i)
             o << "    bi += (JIDX)" << cvt << "((pf[" << i << "] - " << pool.ref(fl->lo[i]) << ") * " << pool.ref(fl->mult_d[i]) << ") * (JIDX)"
               << fl->mult_i[i] << "ULL;\n";
+        if (const char *hx = getenv("FFR_EXPERIMENT_HASH"))   /* EXPERIMENT: scrambled cell order (results are garbage) */
+        {
+            if (*hx == '1')
+                o << "    bi ^= bi >> 11; bi *= 0x9E3779B1u; bi ^= bi >> 15; bi &= (JIDX)" << (fl->cells - 1) << "ULL;\n";
+            else if (*hx == '2')
+                o << "    bi = (bi * 0x9E3779B1u) & (JIDX)" << (fl->cells - 1) << "ULL;\n";
+            else if (*hx == '3')
+                o << "    bi ^= (bi >> 9) & 0x1ffu; bi ^= (bi >> 18) & 0x1ffu;\n";
+        }
         o << "    return bi;\n}\n\n";
         o << "__device__ __forceinline__ u64 jit_json_id(unsigned k)\n{\n    switch (k)\n    {\n";
         for (int k = 0; k < NX; ++k)

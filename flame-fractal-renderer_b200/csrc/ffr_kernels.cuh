@@ -697,6 +697,33 @@ __global__ void __launch_bounds__(FFR_TPB,FFR_REGROUP_MINB) render_kernel_regrou
 
 #define FFR_SMEM_REGROUP_BYTES(D,RCAP,EB) ((16 + 4 + (D) + (RCAP))*FFR_TPB*(EB))
 
+/* K2b: fold K1e's accumulation tile into the buffer. The tile holds the counts of one launch
+   with cell i at position (((i >> g)*mul) mod 2^(k-g)) << g | (i mod 2^g) -- groups of 2^g cells
+   (g = 2: one 32-byte sector of u64 counts) stay together and the groups are scrambled
+   multiplicatively (mul odd: a bijection)
+   that spreads an attractor's strongly patterned cell addresses evenly over the L2 slices
+   (measured: sierpinski@1024^2 1.40e11 -> 1.94e11 REDs/s, the uniform-random rate). The tile is
+   read linearly (coalesced); most of it is zero for a sparse attractor, and only nonzero
+   positions touch the buffer (the inverse map uses mul's inverse mod 2^(k-g)). The tile is left
+   all zero. */
+template <typename W>
+__global__ void fold_acc_kernel(W *__restrict__ acc, W *__restrict__ buffer, u64 cells, uint32_t mul_inv,
+        uint32_t gran)
+{
+    const u64 stride = (u64)gridDim.x*blockDim.x;
+    const uint32_t mask = (uint32_t)((cells - 1) >> gran), low = (1u << gran) - 1u;
+    for (u64 j = (u64)blockIdx.x*blockDim.x + threadIdx.x; j < cells; j += stride)
+    {
+        const W v = acc[j];
+        if (v)
+        {
+            const uint32_t g = (uint32_t)(j >> gran);
+            buffer[((u64)((g*mul_inv) & mask) << gran) | ((uint32_t)j & low)] += v;
+            acc[j] = 0;
+        }
+    }
+}
+
 /* K2: dst += src with the reference's mixed element typing: element 0 of each cell is a
    count (u64 / u32), elements 1..r are colour sums (f64 / f32) (buffer_renderer.hpp:375-391).
    src may be peer memory (multi-GPU reduce over NVLink) or a staged host buffer (-i). */

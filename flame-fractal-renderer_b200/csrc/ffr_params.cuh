@@ -31,6 +31,8 @@ struct RenderParams
                                       trace[it*chain_count + k], ~0 when not plotted */
     u64 chain_first, chain_count, chain_len, last_len, base_seed, bv_limit;
     uint32_t blob_bytes, scatter_mode;
+    void *acc;                     /* K1e: accumulation tile in scrambled cell order (or null), folded
+                                      into `buffer` by fold_acc_kernel after the launch */
 };
 
 /* (size_t)((pf - lo) * mult_d): truncating conversion, buffer_renderer.hpp:202 */

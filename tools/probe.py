@@ -14,6 +14,10 @@ CONFIGS = {
     "sierp3d": ("sierpinski_triangle_3d", [512, 512, 512]),
     "csci": ("csci6360_project", [4096, 4096]),
     "csci8k": ("csci6360_project", [8192, 8192]),
+    "barnsley4k": ("barnsley_fern", [4096, 4096]),
+    "barnsley1k": ("barnsley_fern", [1024, 1024]),
+    "sierp4k": ("sierpinski_triangle", [4096, 4096]),
+    "sierp3d256": ("sierpinski_triangle_3d", [256, 256, 256]),
 }
 
 def main():
