@@ -745,8 +745,9 @@ void jit_maybe(ffr_ctx *ctx, u64 samples)
         return;
     const char *e = getenv("FFR_JIT_MIN_SAMPLES");
     /* ~2 s of NVRTC against ~4e-11 s saved per sample over the interpreter kernels (variation
-       flames); ~1 s against ~2e-12 s per sample for pure-affine flames (K1e over K1) */
-    const double min_samples = (e && *e) ? atof(e) : (ctx->affine_only ? 1e12 : 5e10);
+       flames); ~0.4 s against ~4.5e-12 s per sample for pure-affine flames (K1e 1.85e11/s over K1
+       1.0e11/s); the cubin is cached on disk, so a repeated flame pays nothing */
+    const double min_samples = (e && *e) ? atof(e) : (ctx->affine_only ? 2e11 : 5e10);
     if ((double)samples >= min_samples)
         jit_activate(ctx);
 }
