@@ -142,6 +142,7 @@ struct DeviceState
     int jit_blocks_per_sm = 0;
     void *d_rsl_jit = nullptr;     /* K1c randrsl scratch */
     void *d_acc = nullptr;         /* K1e accumulation tile (scrambled cell order), cells words */
+    unsigned int *d_dir = nullptr; /* K1e compact tile: row directory + allocation counter (last entry) */
 };
 
 typedef void (*render_fn)(const RenderParams);
@@ -602,6 +603,20 @@ bool jit_prepare(ffr_ctx *ctx)
                 cfg.acc_gran = (unsigned)env_int("FFR_ACC_GRAN",bytes <= (32u << 20) ? 0 : sector);
             }
         }
+        /* Compact tile behind a row directory for buffers beyond the TLB reach (fold_dir_kernel):
+           sierpinski_3d@512^3 (1 GiB) 8.2e10 -> see DESIGN.md. Tile <= 192 MiB. */
+        cfg.dir_cap = 0;
+        {
+            const u64 bytes = ctx->cells*ctx->elem;
+            const u64 min_bytes = (u64)env_int("FFR_DIR_MIN_MB",257) << 20;
+            if (!cfg.acc_mul && env_int("FFR_K1E_DIR",1) != 0 && ctx->r == 0 && bytes >= min_bytes &&
+                    ctx->cells % (1u << FFR_DIR_ROW_SHIFT) == 0 && (ctx->cells >> FFR_DIR_ROW_SHIFT) < 0xfffffff0ULL)
+            {
+                const u64 tile_bytes = (u64)env_int("FFR_DIR_TILE_MB",192) << 20;
+                cfg.dir_cap = (unsigned)std::min<u64>(tile_bytes/((u64)ctx->elem << FFR_DIR_ROW_SHIFT),
+                                                      ctx->cells >> FFR_DIR_ROW_SHIFT);
+            }
+        }
         std::string why;
         if (cfg.tpb >= 32 && cfg.tpb <= 1024 && cfg.tpb % 32 == 0)
             ctx->jit_source = ctx->elem == 8 ? jit::generate_affine<double>(ctx->blob,m0,m0_32,cfg,&cfg.npair,why)
@@ -619,6 +634,7 @@ bool jit_prepare(ffr_ctx *ctx)
             }
             ctx->jit_compile_s += secs;
             ctx->jit_note += std::string("K1e pure-affine kernel, ") + (cfg.acc_mul ? "scrambled accumulation tile, " : "") +
+                (cfg.dir_cap ? "compact tile of " + std::to_string(cfg.dir_cap) + " rows, " : std::string()) +
                 std::to_string(cfg.npair) + " table rows, tpb " +
                 std::to_string(cfg.tpb) + ": " + std::to_string(spills) + " spill bytes; ";
             return true;
@@ -733,6 +749,16 @@ int jit_activate(ffr_ctx *ctx)
             CK(cudaMalloc(&ds.d_acc,(size_t)ctx->cells*ctx->elem));
             CK(cudaMemsetAsync(ds.d_acc,0,(size_t)ctx->cells*ctx->elem,ds.stream));
         }
+        if (ctx->jit_cfg.affine && ctx->jit_cfg.dir_cap)
+        {
+            const size_t tile = ((size_t)ctx->jit_cfg.dir_cap << FFR_DIR_ROW_SHIFT)*ctx->elem;
+            const size_t rows = (size_t)(ctx->cells >> FFR_DIR_ROW_SHIFT);
+            CK(cudaMalloc(&ds.d_acc,tile));
+            CK(cudaMemsetAsync(ds.d_acc,0,tile,ds.stream));
+            CK(cudaMalloc(&ds.d_dir,(rows + 1)*sizeof(unsigned int)));
+            CK(cudaMemsetAsync(ds.d_dir,0xff,rows*sizeof(unsigned int),ds.stream));
+            CK(cudaMemsetAsync(ds.d_dir + rows,0,sizeof(unsigned int),ds.stream));
+        }
     }
     ctx->jit_ready = true;
     return FFR_OK;
@@ -775,6 +801,8 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
     prm.blob_bytes = (uint32_t)ctx->blob.size();
     prm.scatter_mode = ctx->scatter_mode;
     prm.acc = ds.d_acc;
+    prm.dir = ds.d_dir;
+    prm.dir_next = ds.d_dir ? ds.d_dir + (ctx->cells >> FFR_DIR_ROW_SHIFT) : nullptr;
     if (chain_len >= (1ULL << 31) - 64)
     {
         ctx->err = "chain length (batch size) must be below 2^31 on the device path";
@@ -814,7 +842,18 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
             ctx->err = "cuLaunchKernel(ffr_jit_render): " + jit::cu_err(a,r);
             return FFR_E_CUDA;
         }
-        if (ds.d_acc && fn == ds.jmod.fn)
+        if (ds.d_dir && fn == ds.jmod.fn)
+        {
+            /* K2c: the compact tile's rows into the buffer */
+            const u64 rows = ctx->cells >> FFR_DIR_ROW_SHIFT;
+            const unsigned fgrid = (unsigned)std::min<u64>((rows + 7)/8,(u64)ds.sm_count*16);
+            if (ctx->elem == 8)
+                fold_dir_kernel<u64><<<fgrid,256,0,ds.stream>>>((u64*)ds.d_acc,(u64*)ds.buffer,ds.d_dir,rows);
+            else
+                fold_dir_kernel<unsigned int><<<fgrid,256,0,ds.stream>>>((unsigned int*)ds.d_acc,(unsigned int*)ds.buffer,ds.d_dir,rows);
+            ++ctx->launches;
+        }
+        else if (ds.d_acc && fn == ds.jmod.fn)
         {
             /* K2b: the launch's scrambled tile into the buffer (reference cell order) */
             uint32_t inv = ctx->jit_cfg.acc_mul;      /* Newton: x <- x*(2 - m*x) doubles the valid bits */
@@ -1040,6 +1079,7 @@ void ffr_cuda_destroy(ffr_ctx *ctx)
         if (ds.d_rsl) cudaFree(ds.d_rsl);
         if (ds.d_rsl_jit) cudaFree(ds.d_rsl_jit);
         if (ds.d_acc) cudaFree(ds.d_acc);
+        if (ds.d_dir) cudaFree(ds.d_dir);
         if (ds.jmod.mod) jit::unload(ds.jmod);
         if (ds.d_stage) cudaFree(ds.d_stage);
         if (ds.own_stream && ds.stream) cudaStreamDestroy(ds.stream);

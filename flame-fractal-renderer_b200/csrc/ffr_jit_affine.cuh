@@ -30,7 +30,10 @@ int -> fp conversion of the selection draw, unconditional min/max selects. Here:
  * s_iter follows from the chain lengths; s_plot = s_iter - (samples not plotted);
  * for L2-resident power-of-two buffers the launch scatters into a tile of its own whose cell
    order is scrambled (JACC_MUL), folded into the buffer afterwards (fold_acc_kernel): an
-   attractor's cell addresses are strongly patterned and load the L2 slices unevenly.
+   attractor's cell addresses are strongly patterned and load the L2 slices unevenly;
+ * for buffers beyond the reach of the address translation (> 256 MiB) the launch scatters into
+   a compact tile of 4 KiB rows allocated on first touch through a row directory (JDIR_CAP,
+   fold_dir_kernel): a sparse attractor's hot rows then span tens of MiB instead of 1 GiB.
 
 Everything else is the reference's arithmetic in the reference's order (-fmad=false), so the
 histogram counts and statistics equal K1's bit for bit (tests/test_gpu_jit.py).
@@ -142,6 +145,27 @@ __device__ __noinline__ JafBad jaf_bad(const RenderParams *prm, const JPAIR *tab
     return o;
 }
 
+#ifdef JDIR_CAP
+/* first touches of a row: allocate its slot in the compact tile (cold) */
+__device__ __noinline__ unsigned jaf_dir_slow(unsigned int *dir, unsigned int *next, unsigned row)
+{
+    unsigned slot = __ldcg(&dir[row]);
+    if (slot == FFR_DIR_EMPTY)
+    {
+        const unsigned old = atomicCAS(&dir[row],FFR_DIR_EMPTY,FFR_DIR_BUSY);
+        if (old == FFR_DIR_EMPTY)
+        {
+            const unsigned mine = atomicAdd(next,1u);
+            slot = mine < JDIR_CAP ? mine : FFR_DIR_DIRECT;
+            atomicExch(&dir[row],slot);
+        }
+        else
+            slot = old;     /* BUSY: this sample goes into the buffer; or the winner's slot */
+    }
+    return slot;
+}
+#endif
+
 /* MODES = false: plain RED scatter. MODES = true: prm.scatter_mode honoured (warp-aggregated,
    discard, trace), used by the scatter diagnostics and the attractor-replay roofline. */
 template <bool MODES>
@@ -165,7 +189,7 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
 
     W *col = rng_base + tid, *rcol = rsl_base + tid;
     W *__restrict__ buffer = (W*)prm.buffer;
-#ifdef JACC_MUL
+#if defined(JACC_MUL) || defined(JDIR_CAP)
     W *__restrict__ acc = (W*)prm.acc;
 #endif
     const bool warp_agg = MODES && prm.scatter_mode == FFR_SCATTER_WARP_AGG;
@@ -319,6 +343,23 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
                         if (!MODES)
                             cell = acc + ((((((unsigned)bi >> JACC_GRAN)*JACC_MUL) & JACC_MASK) << JACC_GRAN) |
                                           ((unsigned)bi & ((1u << JACC_GRAN) - 1u)));
+#endif
+#ifdef JDIR_CAP
+                        /* compact tile: rows of 512 cells allocated on first touch (fold_dir_kernel).
+                           The directory is read through L1: a stale line can only say "not allocated
+                           yet", which sends the lane to the coherent slow path. */
+                        if (!MODES)
+                        {
+                            const unsigned row = (unsigned)(bi >> FFR_DIR_ROW_SHIFT);
+                            unsigned slot = __ldca(&prm.dir[row]);
+                            if (slot >= FFR_DIR_DIRECT)
+                                slot = jaf_dir_slow(prm.dir,prm.dir_next,row);
+                            if (slot < FFR_DIR_DIRECT)
+                            {
+                                unsigned off = (unsigned)bi & ((1u << FFR_DIR_ROW_SHIFT) - 1u);
+                                cell = acc + (((u64)slot << FFR_DIR_ROW_SHIFT) | off);
+                            }
+                        }
 #endif
                         if (!MODES)
                             hist_add(cell,1u); /* :211-215 */

@@ -46,6 +46,7 @@ struct Config
     int npair = 0;          /* K1e: 16-byte rows of the per-xform coefficient table */
     unsigned acc_mul = 0;   /* K1e: scramble multiplier of the accumulation tile (0: scatter into the buffer) */
     unsigned acc_gran = 0;  /* K1e: log2 of the cells that stay together in the tile */
+    unsigned dir_cap = 0;   /* K1e: rows of the compact tile (0: none); excludes acc_mul */
 };
 
 struct Api
@@ -658,6 +659,8 @@ std::string generate_affine(const std::vector<unsigned char> &blobv, const u64 *
         if (cfg.acc_mul)
             h << "#define JACC_MUL " << cfg.acc_mul << "u\n#define JACC_MASK " << ((fl->cells - 1) >> cfg.acc_gran)
               << "u\n#define JACC_GRAN " << cfg.acc_gran << "\n";
+        if (cfg.dir_cap)
+            h << "#define JDIR_CAP " << cfg.dir_cap << "u\n";
         h << "\n";
         o << "/* XForm::applyIteration for every xform of the flame; tb = coefficient table + xform index */\n";
         if (p_nz)
@@ -710,15 +713,6 @@ std::string generate_affine(const std::vector<unsigned char> &blobv, const u64 *
         for (int i = 1; i < D; ++i)
             o << "    bi += (JIDX)" << cvt << "((pf[" << i << "] - " << pool.ref(fl->lo[i]) << ") * " << pool.ref(fl->mult_d[i]) << ") * (JIDX)"
               << fl->mult_i[i] << "ULL;\n";
-        if (const char *hx = getenv("FFR_EXPERIMENT_HASH"))   /* EXPERIMENT: scrambled cell order (results are garbage) */
-        {
-            if (*hx == '1')
-                o << "    bi ^= bi >> 11; bi *= 0x9E3779B1u; bi ^= bi >> 15; bi &= (JIDX)" << (fl->cells - 1) << "ULL;\n";
-            else if (*hx == '2')
-                o << "    bi = (bi * 0x9E3779B1u) & (JIDX)" << (fl->cells - 1) << "ULL;\n";
-            else if (*hx == '3')
-                o << "    bi ^= (bi >> 9) & 0x1ffu; bi ^= (bi >> 18) & 0x1ffu;\n";
-        }
         o << "    return bi;\n}\n\n";
         o << "__device__ __forceinline__ u64 jit_json_id(unsigned k)\n{\n    switch (k)\n    {\n";
         for (int k = 0; k < NX; ++k)

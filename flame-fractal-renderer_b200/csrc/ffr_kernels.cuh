@@ -724,6 +724,38 @@ __global__ void fold_acc_kernel(W *__restrict__ acc, W *__restrict__ buffer, u64
     }
 }
 
+/* K2c: fold K1e's COMPACT tile into the buffer. For buffers whose span exceeds what the GPU's
+   address translation covers (measured: a fixed 8 MB hot set takes 1.9e11 RED/s while its span
+   is <= 256 MiB and 4.3-5.4e10 at 512 MiB-1 GiB, tools/micro/red_span.cu) the kernel scatters
+   into rows of 512 cells allocated on first touch in a tile of <= 192 MiB; dir[row] is the
+   row's slot. One warp per row; the tile is left all zero, the directory stays (rows keep their
+   slots for the context's lifetime). */
+template <typename W>
+__global__ void fold_dir_kernel(W *__restrict__ tile, W *__restrict__ buffer, const unsigned int *__restrict__ dir,
+        u64 rows)
+{
+    const u64 warps = ((u64)gridDim.x*blockDim.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    for (u64 row = ((u64)blockIdx.x*blockDim.x + threadIdx.x) >> 5; row < rows; row += warps)
+    {
+        const unsigned int slot = dir[row];
+        if (slot >= FFR_DIR_DIRECT)
+            continue;
+        W *t = tile + ((u64)slot << FFR_DIR_ROW_SHIFT);
+        W *b = buffer + (row << FFR_DIR_ROW_SHIFT);
+#pragma unroll 4
+        for (unsigned i = lane; i < (1u << FFR_DIR_ROW_SHIFT); i += 32u)
+        {
+            const W v = t[i];
+            if (v)
+            {
+                b[i] += v;
+                t[i] = 0;
+            }
+        }
+    }
+}
+
 /* K2: dst += src with the reference's mixed element typing: element 0 of each cell is a
    count (u64 / u32), elements 1..r are colour sums (f64 / f32) (buffer_renderer.hpp:375-391).
    src may be peer memory (multi-GPU reduce over NVLink) or a staged host buffer (-i). */

@@ -31,9 +31,17 @@ struct RenderParams
                                       trace[it*chain_count + k], ~0 when not plotted */
     u64 chain_first, chain_count, chain_len, last_len, base_seed, bv_limit;
     uint32_t blob_bytes, scatter_mode;
-    void *acc;                     /* K1e: accumulation tile in scrambled cell order (or null), folded
-                                      into `buffer` by fold_acc_kernel after the launch */
+    void *acc;                     /* K1e: accumulation tile (or null): scrambled cell order, folded into
+                                      `buffer` by fold_acc_kernel after the launch; or compact rows */
+    unsigned int *dir;             /* K1e, buffers beyond the TLB reach: row directory of the compact
+                                      tile (fold_dir_kernel), and its allocation counter */
+    unsigned int *dir_next;
 };
+
+#define FFR_DIR_EMPTY  0xffffffffu   /* row not seen yet */
+#define FFR_DIR_BUSY   0xfffffffeu   /* being allocated by another thread: scatter into the buffer */
+#define FFR_DIR_DIRECT 0xfffffffdu   /* tile full: this row is scattered into the buffer */
+#define FFR_DIR_ROW_SHIFT 9          /* 512 cells (4 KiB of u64) per row */
 
 /* (size_t)((pf - lo) * mult_d): truncating conversion, buffer_renderer.hpp:202 */
 __device__ __forceinline__ u64 to_index(double v) { return __double2ull_rz(v); }

@@ -138,3 +138,43 @@ def test_flames_outside_k1e_keep_working(ffr):
     flame-specialised kernel instead, same bits"""
     st, info = compare(ffr, flames.divergent_flame(), chains=300, chain_len=300)
     assert info["active"] and not is_k1e(info)
+
+
+@pytest.fixture
+def force_compact_tile(monkeypatch):
+    """The compact tile (row directory) is meant for buffers beyond 256 MiB; force it onto the
+    small test buffers. The settings are read when the kernel is generated."""
+    def setter(tile_mb=192):
+        monkeypatch.setenv("FFR_DIR_MIN_MB", "0")
+        monkeypatch.setenv("FFR_K1E_SCRAMBLE", "0")
+        monkeypatch.setenv("FFR_DIR_TILE_MB", str(tile_mb))
+    return setter
+
+
+def test_compact_tile(ffr, examples, force_compact_tile):
+    force_compact_tile()
+    for text in (examples.example_json("sierpinski_triangle_3d", size=[64, 64, 64]),
+                 examples.example_json("barnsley_fern", size=[512, 512])):
+        _, info = compare(ffr, text, chains=2000, chain_len=500)
+        assert is_k1e(info) and "compact tile" in info["message"], info
+
+
+def test_compact_tile_overflow_and_repeated_renders(ffr, examples, force_compact_tile):
+    """1 MiB tile = 256 rows of 512 cells; the fern at 1024x512 touches more rows than that: the
+    rest is scattered into the buffer directly. Rows keep their slots across render calls."""
+    force_compact_tile(tile_mb=1)
+    text = examples.example_json("barnsley_fern", size=[1024, 512])
+    fl = ffr.Flame(text)
+    bufs = []
+    for jit in (ffr.JIT_OFF, ffr.JIT_ON):
+        r = ffr.BufferRenderer(fl, jit=jit)
+        if jit == ffr.JIT_ON:
+            assert "compact tile of 256 rows" in r.jit_info["message"], r.jit_info
+        for k in range(3):
+            assert r.render_chains(1000 * k, 1000, 400, base_seed=3)
+        bufs.append((r.read_buffer(), r.stats))
+        r.close()
+    assert np.array_equal(bufs[0][0], bufs[1][0])
+    for k in ("s_iter", "s_plot", "xf_dist", "pt_min", "pt_max"):
+        assert bufs[0][1][k] == bufs[1][1][k], k
+    assert np.count_nonzero(bufs[1][0].reshape(-1, 512).any(axis=1)) > 256   # it did overflow
