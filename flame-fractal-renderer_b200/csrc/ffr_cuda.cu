@@ -174,6 +174,7 @@ struct ffr_ctx
     /* K1c, the run-time compiled flame-specialised kernel (ffr_jit_kernel.cuh) */
     uint32_t jit_mode = 0;         /* 0 auto (lazy, large renders), 1 off, 2 on at create */
     bool jit_eligible = false, jit_ready = false, jit_failed = false, jit_cached = false;
+    bool jit_cache_probed = false;   /* auto mode looked for this flame's cubin in the cache already */
     jit::Config jit_cfg;
     size_t jit_smem = 0;
     double jit_compile_s = 0.0;
@@ -560,7 +561,7 @@ bool jit_supported(const ffr_ctx *ctx)
 }
 
 /* generate the source for this flame and compile it (no device needed) */
-bool jit_prepare(ffr_ctx *ctx)
+bool jit_prepare(ffr_ctx *ctx, bool cache_only = false)
 {
     if (!ctx->jit_cubin.empty())
         return true;
@@ -627,7 +628,7 @@ bool jit_prepare(ffr_ctx *ctx)
             ctx->jit_smem = (size_t)32*cfg.tpb*ctx->elem + (size_t)cfg.npair*ctx->num_xforms*2*ctx->elem;
             long spills = 0;
             double secs = 0.0;
-            if (!jit::compile(ctx->jit_source,ctx->jit_cubin,ctx->jit_err,&secs,&ctx->jit_cached,&spills))
+            if (!jit::compile(ctx->jit_source,ctx->jit_cubin,ctx->jit_err,&secs,&ctx->jit_cached,&spills,cache_only))
             {
                 ctx->jit_cubin.clear();
                 return false;
@@ -686,7 +687,7 @@ bool jit_prepare(ffr_ctx *ctx)
                                          : jit::generate<float>(ctx->blob,ctx->colors,m0,m0_32,cfg);
         long spills = 0;
         double secs = 0.0;
-        if (!jit::compile(ctx->jit_source,ctx->jit_cubin,ctx->jit_err,&secs,&ctx->jit_cached,&spills))
+        if (!jit::compile(ctx->jit_source,ctx->jit_cubin,ctx->jit_err,&secs,&ctx->jit_cached,&spills,cache_only))
         {
             ctx->jit_cubin.clear();
             return false;
@@ -776,6 +777,22 @@ void jit_maybe(ffr_ctx *ctx, u64 samples)
     const double min_samples = (e && *e) ? atof(e) : (ctx->affine_only ? 2e11 : 5e10);
     if ((double)samples >= min_samples)
         jit_activate(ctx);
+    else if (!ctx->jit_cache_probed && env_int("FFR_JIT_USE_CACHED",1) != 0)
+    {
+        ctx->jit_cache_probed = true;
+        /* a smaller render: the compiled kernel only if this flame's cubin is already in the
+           process or disk cache (an earlier run paid for it); loading it takes milliseconds */
+        const std::string note = ctx->jit_note;
+        if (jit_prepare(ctx,true))
+            jit_activate(ctx);
+        else
+        {
+            ctx->jit_err.clear();
+            ctx->jit_note = note;
+            ctx->jit_cubin.clear();
+            ctx->jit_cfg = jit::Config();
+        }
+    }
 }
 
 int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_count, u64 chain_len,

@@ -793,7 +793,7 @@ inline const std::vector<Shim> &headers()
 
 /* source -> sm_100a cubin. Needs no GPU. */
 inline bool compile(const std::string &src, std::vector<char> &cubin, std::string &err, double *seconds,
-        bool *from_cache, long *spill_bytes)
+        bool *from_cache, long *spill_bytes, bool cache_only = false)
 {
     /* the last 8 bytes of a cached entry hold the kernel's register spill bytes (ptxas -v) */
     static std::map<u64,std::vector<char>> mem_cache;
@@ -858,6 +858,11 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
                 return true;
             }
         }
+    }
+    if (cache_only)
+    {
+        err = "not in the kernel cache";
+        return false;
     }
     std::vector<const char*> hn, ht;
     std::vector<std::string> texts;

@@ -178,3 +178,42 @@ def test_compact_tile_overflow_and_repeated_renders(ffr, examples, force_compact
     for k in ("s_iter", "s_plot", "xf_dist", "pt_min", "pt_max"):
         assert bufs[0][1][k] == bufs[1][1][k], k
     assert np.count_nonzero(bufs[1][0].reshape(-1, 512).any(axis=1)) > 256   # it did overflow
+
+
+def test_cli_jit_affine_vs_oracle(ffr, po, examples, tmp_path):
+    """ffr-buf.out --jit on a pure-affine flame runs K1e (accumulation tile + fold): the buffer
+    file equals the oracle's, and -i still adds on top of it."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(ffr.LIB_PATH), "ffr-buf.out")
+    flame = tmp_path / "fern.json"
+    flame.write_text(examples.example_json("barnsley_fern", size=[256, 128]))
+    out1, out2 = tmp_path / "a.buf", tmp_path / "b.buf"
+    p = subprocess.run([exe, "-f", str(flame), "-o", str(out1), "-s", "1500000", "-b", "1000",
+                        "--seed", "5", "--jit"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    a = np.fromfile(out1, dtype=np.uint64)
+    fl = ffr.Flame(flame.read_text())
+    want, _, _ = po.oracle_render_samples(fl, 1_500_000, 1000, base_seed=5, nthreads=8)
+    assert np.array_equal(a, want)
+    p = subprocess.run([exe, "-f", str(flame), "-i", str(out1), "-o", str(out2), "-s", "1500000",
+                        "-b", "1000", "--seed", "5", "--jit"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert np.array_equal(np.fromfile(out2, dtype=np.uint64), 2 * a)
+
+
+def test_two_devices_k1e(ffr, po, examples):
+    """K1e on a two-device context: a tile per device, folded before the peer-memory reduce."""
+    if ffr.lib().ffr_cuda_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    fl = ffr.Flame(examples.example_json("sierpinski_triangle", size=[256, 256]))
+    r = ffr.BufferRenderer(fl, devices=[0, 1], jit=ffr.JIT_ON)
+    assert is_k1e(r.jit_info)
+    calls = []
+    assert r.render(3_000_000, 1000, base_seed=8, progress=lambda d, t: calls.append((d, t)))
+    got, st = r.read_buffer(), r.stats
+    r.close()
+    want, ost, _ = po.oracle_render_samples(fl, 3_000_000, 1000, base_seed=8, nthreads=8)
+    assert np.array_equal(got, want)
+    assert_stats_equal(st, ost)
+    assert calls and calls[-1][0] == calls[-1][1]

@@ -105,10 +105,26 @@ def test_unsupported_flame_fails_loudly(ffr):
         ffr.BufferRenderer(ffr.Flame(flames.many_xforms_flame(20)), jit=ffr.JIT_ON)
 
 
-def test_auto_mode_is_lazy(ffr, examples):
-    r = ffr.BufferRenderer(ffr.Flame(examples.example_json("csci6360_project", size=[96, 54])))
+def test_auto_mode_is_lazy(ffr, examples, monkeypatch):
+    text = examples.example_json("csci6360_project", size=[100, 50])   # a size no other test compiles
+    monkeypatch.setenv("FFR_JIT_NO_DISK_CACHE", "1")
+    r = ffr.BufferRenderer(ffr.Flame(text))
     r.render(100000, 1000)
     assert not r.jit_info["active"]     # small render: interpreter kernel, nothing compiled
+    b0 = r.read_buffer()
     r.jit_enable()
     assert r.jit_info["active"] and "jx_0" in r.jit_source
+    r.close()
+    # the cubin is in the process cache now: auto mode takes it even for a small render
+    monkeypatch.setenv("FFR_JIT_USE_CACHED", "1")
+    r = ffr.BufferRenderer(ffr.Flame(text))
+    r.render(100000, 1000)
+    assert r.jit_info["active"] and r.jit_info["from_cache"]
+    assert np.array_equal(r.read_buffer(), b0)
+    r.close()
+    # ... unless told not to
+    monkeypatch.setenv("FFR_JIT_USE_CACHED", "0")
+    r = ffr.BufferRenderer(ffr.Flame(text))
+    r.render(100000, 1000)
+    assert not r.jit_info["active"]
     r.close()
