@@ -155,3 +155,44 @@ def test_simplifier_output_shapes(ffr):
     # flames K1e does not cover fall back to the general generator
     src, _ = ffr.jit_compile(ffr.Flame(flames.divergent_flame()))
     assert "ffr_jit_affine.cuh" not in src
+
+
+def test_flames_k1e_refuses(ffr):
+    """Outside K1e's proof obligations the general generator is used (same results, slower):
+    coefficients too large to prove every intermediate finite through the unchecked settle
+    iterations, bounds beyond the bad value threshold (in-bounds must imply not-bad), xforms of
+    different shape, colours, a final xform."""
+    import json
+
+    def kernel_of(fl):
+        try:
+            src, _ = ffr.jit_compile(ffr.Flame(json.dumps(fl)))
+        except ffr.FfrError as e:
+            if "libnvrtc not found" in str(e):
+                pytest.skip("no NVRTC on this machine")
+            raise
+        return "K1e" if "ffr_jit_affine.cuh" in src else "general"
+
+    base = json.loads(flames.affine_flame(pre="general", post="identity"))
+    assert kernel_of(base) == "K1e"
+    big = json.loads(json.dumps(base))
+    big["xforms"][0]["pre_affine"]["A"][0][0] = 3.0e6
+    assert kernel_of(big) == "general"
+    wide = json.loads(json.dumps(base))
+    wide["bounds"][0] = [-1.0e21, 1.0]      # the flame model already refuses such bounds
+    with pytest.raises(ffr.FfrError):
+        kernel_of(wide)
+    ragged = json.loads(json.dumps(base))
+    ragged["xforms"][1]["variations"].append({"name": "linear", "weight": 0.25})
+    assert kernel_of(ragged) == "general"
+    col = json.loads(json.dumps(base))
+    col["color_dimensions"] = 1
+    col["xforms"][0]["color"] = [0.5]
+    assert kernel_of(col) == "general"
+    fin = json.loads(json.dumps(base))
+    fin["final_xform"] = {"variations": [{"name": "linear", "weight": 1.0}]}
+    assert kernel_of(fin) == "general"
+    # mildly expanding maps are fine: alpha^55 stays far below DBL_MAX
+    mild = json.loads(json.dumps(base))
+    mild["xforms"][0]["pre_affine"]["A"][0][0] = 50.0
+    assert kernel_of(mild) == "K1e"
