@@ -87,7 +87,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -96,18 +96,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: only samples taken from here to stop() are reported
+        (the sampler itself is started before the warm-up so that nvidia-smi's start-up time
+        does not eat the region)."""
+        self.t0 = time.monotonic()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.monotonic()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        window = [(ts, ln) for ts, ln in list(self.lines) if t0 <= ts <= t1]
+        if not window:      # region shorter than one sampling period: the nearest samples
+            window = list(self.lines)[-2:]
+        for ts, ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -184,7 +195,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--waves", type=int, default=4,
                     help="chain groups per resident block and step")
-    ap.add_argument("--ref-samples", type=int, default=20_000_000,
+    ap.add_argument("--ref-samples", type=int, default=100_000_000,
                     help="bounded CPU sample per step for the reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scatter", type=int, default=0)
@@ -254,7 +265,10 @@ def main():
     def reduce_to_rank0():
         sharding.reduce_buffer(buf, cells, cell, dst=0)
 
-    # ---- warm-up (>= 3 steps) ----
+    # ---- warm-up (>= 3 steps); the clock sampler starts here, reports the timed region only ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for w in range(max(args.warmup, 0)):
         launch_step(1_000_000 + w)
     barrier()
@@ -263,13 +277,11 @@ def main():
     launches0 = rend.launches
 
     # ---- timed region: K steps (+ the final buffer reduce for N > 1) ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     ev_k = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    sampler.mark()
     ev0.record(stream)
     ev_k[0].record(stream)
     for k in range(args.steps):
