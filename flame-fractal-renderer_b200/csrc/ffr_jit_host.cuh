@@ -293,13 +293,16 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
     for (int i = 0; i < 16; ++i)
         h << (i ? "," : "") << m0_32[i] << "u";
     h << "}\n";
+    if (getenv("FFR_SC_XOR") && *getenv("FFR_SC_XOR") == '0')
+        h << "#define FFR_SC_XOR 0\n";
     if (getenv("FFR_JIT_ROT_STATIC") && *getenv("FFR_JIT_ROT_STATIC") == '1')
         h << "#define JROT_STATIC 1\n";
     if (cfg.async)
         h << "#define JRSL_SMEM " << (fl->uses_rng ? 1 : 0) << "\n"
           << (fl->uses_rng ? "" : "#define FFR_RSL_LOAD(p) __ldcg(p)\n");
     if (cfg.async)
-        h << "#define FFR_SINCOS_OOL 1\n#define JPOLAR(P,need,x,y) P = polar_fill_ool<JT>(need,x,y)\n";
+        h << ((getenv("FFR_JIT_SC_INLINE") && *getenv("FFR_JIT_SC_INLINE") == '1') ? "" : "#define FFR_SINCOS_OOL 1\n")
+          << "#define JPOLAR(P,need,x,y) P = polar_fill_ool<JT>(need,x,y)\n";
     else
         h << "#define JPOLAR(P,need,x,y) polar_fill(P,need,x,y)\n";
     h << "#include \"ffr_params.cuh\"\n";
