@@ -10,6 +10,7 @@ point that computes needs an sm_100 device and fails loudly without one.
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ffr_kernels.cuh"
@@ -1041,6 +1042,21 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
         }
     }
     ctx->devs.resize(ndev);
+    if (ndev > 1)
+    {
+        /* creating a device's primary context takes a good part of a second: all of them at
+           once, from one thread each (errors surface in the sequential set-up below) */
+        std::vector<std::thread> warm;
+        for (int i = 0; i < ndev; ++i)
+        {
+            const int dev = devices ? devices[i] : i;
+            if (dev >= 0 && dev < avail)
+                warm.emplace_back([dev]() { if (cudaSetDevice(dev) == cudaSuccess) cudaFree(0); });
+        }
+        for (std::thread &t : warm)
+            t.join();
+        cudaGetLastError();
+    }
     for (int i = 0; i < ndev; ++i)
     {
         int dev = devices ? devices[i] : i;

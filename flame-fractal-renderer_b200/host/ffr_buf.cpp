@@ -30,6 +30,7 @@ options:
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -202,6 +203,17 @@ int main(int argc, char **argv)
             return 1;
         }
     }
+    /* FFR_TIMING=1: wall-clock of the phases on stderr (additive; off by default so that the
+       report keeps the reference's lines) */
+    const bool timing = getenv("FFR_TIMING") && *getenv("FFR_TIMING") == '1';
+    const auto t_start = std::chrono::steady_clock::now();
+    auto phase = [&](const char *name)
+    {
+        if (timing)
+            std::cerr << "timing: " << name << " at "
+                      << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count()
+                      << " s" << std::endl;
+    };
     char err[512];
     ffr_flame *flame = ffr_flame_from_json_ex(text.data(),text.size(),nullptr,0,arg_elem,err,sizeof(err));
     if (!flame)
@@ -228,6 +240,7 @@ int main(int argc, char **argv)
         std::cerr << "ERROR: " << err << std::endl;
         return 1;
     }
+    phase("context created");
     const size_t bytes = ffr_cuda_buffer_bytes(ctx);
     std::cerr << "buffer: " << bytes << " bytes, ";
 #if __BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__
@@ -327,12 +340,14 @@ int main(int argc, char **argv)
         std::cerr << std::endl;
     }
 
+    phase("render and report done");
     std::cerr << "writing output" << std::endl;
     if (ffr_cuda_read_buffer(ctx,host.data(),bytes) != FFR_OK)
     {
         std::cerr << "ERROR: " << ffr_cuda_last_error(ctx) << std::endl;
         return 1;
     }
+    phase("buffer reduced and read back");
     if (arg_output == "-")
     {
         std::cout.write(host.data(),bytes);
@@ -352,7 +367,9 @@ int main(int argc, char **argv)
             return 1;
         }
     }
+    phase("output written");
     ffr_cuda_destroy(ctx);
     ffr_flame_free(flame);
+    phase("context destroyed");
     return 0;
 }
