@@ -56,7 +56,7 @@ UNIT = "samples/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per PLOTTED sample of the render kernel, from the
 # committed `ncu --set full` captures (profiles/README.md); traffic per launch = this x plotted
 NCU_DRAM_BYTES_PER_PLOTTED = {
-    "csci6360_4096": (0.2551e9 + 1.9064e9) / 261.7e6,   # profiles/r1_k1d_csci4096 (329.8e6 samples)
+    "csci6360_4096": (0.4210e9 + 3.8049e9) / 500.0e6,   # profiles/r1_k1d_csci4096_sincos (500.0e6 plotted = RED sectors)
     "tkoz_test3_4096": (1.8337e9 + 6.6085e9) / 327.7e6,  # profiles/r1_k1d_tkoz3_4096
     "sierpinski3d_512": (8.99e6 + 0.006e6) / 1862.3e6,  # profiles/r1_k1e_sierp3d_512_compact_tile
     "barnsley_2048": (25.83e6 + 0.008e6) / 1862.3e6,    # profiles/r1_k1e_barnsley2048
