@@ -82,6 +82,30 @@ def test_add_buffer_resume(ffr, po, examples):
     assert r.bytes == first.nbytes
 
 
+def test_segmented_render_equals_single_launch(ffr, examples):
+    """ffr_cuda_render with a progress callback cuts a large render into several launches (each
+    at least four waves of the resident chains); which launch runs a chain changes nothing:
+    counts and statistics equal those of the single launch without a callback."""
+    fl = ffr.Flame(examples.example_json("sierpinski_triangle", size=[128, 128]))
+    r = ffr.BufferRenderer(fl, jit=ffr.JIT_OFF)
+    L = 256
+    samples = (r.resident_chains * 9 + 7) * L + 31      # > 2 segments, ragged last chain
+    calls = []
+    assert r.render(samples, L, base_seed=3, progress=lambda d, t: calls.append((d, t)))
+    seg_buf, seg_st = r.read_buffer(), r.stats
+    r.close()
+    assert len(calls) >= 2 and calls[-1][0] == calls[-1][1] == (samples + L - 1) // L
+    assert all(a[0] < b[0] for a, b in zip(calls, calls[1:]))
+    r = ffr.BufferRenderer(fl, jit=ffr.JIT_OFF)
+    assert r.render(samples, L, base_seed=3)
+    one_buf, one_st = r.read_buffer(), r.stats
+    r.close()
+    assert np.array_equal(seg_buf, one_buf)
+    for k in ("s_iter", "s_plot", "xf_dist", "pt_min", "pt_max", "n_bad"):
+        assert seg_st[k] == one_st[k], k
+    assert seg_st["s_iter"] == samples
+
+
 def test_histogram_sum_max_and_progress(ffr, examples):
     fl = ffr.Flame(examples.example_json("sierpinski_triangle", size=[128, 128]))
     r = ffr.BufferRenderer(fl)
