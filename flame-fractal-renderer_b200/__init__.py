@@ -132,6 +132,8 @@ ABI = {
     "ffr_var_name": (C.c_char_p, [C.c_uint32]),
     "ffr_var_op_from_name": (C.c_uint32, [C.c_char_p]),
     "ffr_reference_batch_size": (C.c_uint64, [C.c_uint64]),
+    "ffr_flame_json_echo": (C.c_size_t, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
+                                         C.c_char_p, C.c_size_t]),
     # ffr_cuda.h
     "ffr_cuda_version": (C.c_char_p, []),
     "ffr_cuda_device_count": (C.c_int, []),
@@ -267,6 +269,19 @@ class Flame:
         if self.desc.has_final:
             xfs.append(self.desc.final_xform.contents)
         return all(xf.vars[k].op in ops for xf in xfs for k in range(xf.num_vars))
+
+
+def flame_json_echo(text):
+    """The text after `flame: ` on the reference's stderr (ffr_buf.cpp:129)."""
+    if isinstance(text, str):
+        text = text.encode()
+    err = C.create_string_buffer(512)
+    n = lib().ffr_flame_json_echo(text, len(text), None, 0, err, len(err))
+    if not n:
+        raise FfrError(err.value.decode())
+    out = C.create_string_buffer(n + 1)
+    lib().ffr_flame_json_echo(text, len(text), out, n + 1, None, 0)
+    return out.value.decode()
 
 
 def stats_to_dict(st, dims, n_ids):

@@ -215,6 +215,20 @@ int main(int argc, char **argv)
                       << " s" << std::endl;
     };
     char err[512];
+    {
+        /* the reference echoes the parsed flame before anything else (ffr_buf.cpp:129) */
+        err[0] = 0;
+        const size_t n = ffr_flame_json_echo(text.data(),text.size(),nullptr,0,err,sizeof(err));
+        if (!n)
+        {
+            std::cerr << "ERROR: " << err << std::endl;
+            return 1;
+        }
+        std::string echo(n + 1,'\0');
+        ffr_flame_json_echo(text.data(),text.size(),&echo[0],echo.size(),nullptr,0);
+        echo.resize(n);
+        std::cerr << "flame: " << echo << std::endl;
+    }
     ffr_flame *flame = ffr_flame_from_json_ex(text.data(),text.size(),nullptr,0,arg_elem,err,sizeof(err));
     if (!flame)
     {
@@ -289,6 +303,10 @@ int main(int argc, char **argv)
         prog.t1 = t1;
         prog.samples = arg_samples;
         prog.batch = arg_batch_size;
+        /* cb_thread of BufferRenderer::render (ffr_buf.cpp:214-218): one line per worker; the
+           workers here are the devices */
+        for (int g = 0; g < arg_gpus; ++g)
+            std::cerr << "started thread " << g << " (cuda:" << g << ")" << std::endl;
         static ffr_stats stats;
         int rc = ffr_cuda_render(ctx,arg_samples,arg_batch_size,arg_seed,arg_bad_values,
             progress_cb,&prog,&stats);

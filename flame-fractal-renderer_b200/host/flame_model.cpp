@@ -915,6 +915,24 @@ uint32_t ffr_var_op_from_name(const char *name)
     return 0;
 }
 
+size_t ffr_flame_json_echo(const char *text, size_t len, char *out, size_t outlen,
+        char *err, size_t errlen)
+{
+    try
+    {
+        std::string d;
+        Json::parse(text,len).dump(d);
+        if (out && outlen)
+            snprintf(out,outlen,"%s",d.c_str());
+        return d.size();
+    }
+    catch (std::exception& e)
+    {
+        setErr(err,errlen,e.what());
+        return 0;
+    }
+}
+
 uint64_t ffr_reference_batch_size(uint64_t samples)
 {
     uint64_t guess = (samples+255) >> 8;

@@ -14,7 +14,10 @@ Errors are thrown as ffr::JsonError with the reference's message texts.
 #pragma once
 
 #include <cerrno>
+#include <charconv>
+#include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -459,6 +462,141 @@ public:
         if (!isObject())
             throw JsonError("Json::set(): not an object");
         obj[key] = v;
+    }
+
+    // Compact serialisation as `os << nlohmann::json` prints it (the "flame:" echo of
+    // ffr_buf.cpp:129, via utils/json.cpp:203-207): keys in std::map order, no whitespace,
+    // integers in decimal, doubles as the shortest digits that round-trip laid out by
+    // nlohmann's rule (plain notation for decimal exponents -4 < n <= 15 with a trailing
+    // ".0" on whole numbers, d.ddde[+-]XX otherwise), non-finite as null.
+    void dump(std::string& out) const
+    {
+        switch (type)
+        {
+        case Null: out += "null"; break;
+        case Bool: out += b ? "true" : "false"; break;
+        case Int: out += std::to_string(i); break;
+        case UInt: out += std::to_string(u); break;
+        case Float: dumpFloat(out,f); break;
+        case String: dumpString(out,s); break;
+        case Array:
+            out += '[';
+            for (size_t k = 0; k < arr.size(); ++k)
+            {
+                if (k) out += ',';
+                arr[k].dump(out);
+            }
+            out += ']';
+            break;
+        case Object:
+        {
+            out += '{';
+            bool first = true;
+            for (auto& kv : obj)
+            {
+                if (!first) out += ',';
+                first = false;
+                dumpString(out,kv.first);
+                out += ':';
+                kv.second.dump(out);
+            }
+            out += '}';
+            break;
+        }
+        }
+    }
+
+    static void dumpString(std::string& out, const std::string& v)
+    {
+        out += '"';
+        for (unsigned char c : v)
+        {
+            switch (c)
+            {
+            case '"': out += "\\\""; break;
+            case '\\': out += "\\\\"; break;
+            case '\b': out += "\\b"; break;
+            case '\f': out += "\\f"; break;
+            case '\n': out += "\\n"; break;
+            case '\r': out += "\\r"; break;
+            case '\t': out += "\\t"; break;
+            default:
+                if (c < 0x20)
+                {
+                    char esc[8];
+                    snprintf(esc,sizeof(esc),"\\u%04x",(unsigned)c);
+                    out += esc;
+                }
+                else
+                    out += (char)c;
+            }
+        }
+        out += '"';
+    }
+
+    static void dumpFloat(std::string& out, double v)
+    {
+        if (!std::isfinite(v))
+        {
+            out += "null";
+            return;
+        }
+        if (v == 0.0)
+        {
+            out += std::signbit(v) ? "-0.0" : "0.0";
+            return;
+        }
+        if (v < 0)
+        {
+            out += '-';
+            v = -v;
+        }
+        // shortest round-trip digits d1 d2 .. dk and decimal exponent: v = 0.d1..dk * 10^n
+        char sci[40];
+        auto res = std::to_chars(sci,sci + sizeof(sci),v,std::chars_format::scientific);
+        std::string t(sci,res.ptr);
+        const size_t epos = t.find('e');
+        std::string digits;
+        for (size_t k = 0; k < epos; ++k)
+            if (t[k] != '.')
+                digits += t[k];
+        const int n = atoi(t.c_str() + epos + 1) + 1;
+        const int k = (int)digits.size();
+        const int min_exp = -4, max_exp = 15;
+        if (k <= n && n <= max_exp)
+        {
+            out += digits;
+            out.append((size_t)(n - k),'0');
+            out += ".0";
+        }
+        else if (0 < n && n <= max_exp)
+        {
+            out.append(digits,0,(size_t)n);
+            out += '.';
+            out.append(digits,(size_t)n,std::string::npos);
+        }
+        else if (min_exp < n && n <= 0)
+        {
+            out += "0.";
+            out.append((size_t)(-n),'0');
+            out += digits;
+        }
+        else
+        {
+            out += digits[0];
+            if (k > 1)
+            {
+                out += '.';
+                out.append(digits,1,std::string::npos);
+            }
+            out += 'e';
+            int e = n - 1;
+            out += e < 0 ? '-' : '+';
+            if (e < 0) e = -e;
+            char eb[8];
+            snprintf(eb,sizeof(eb),"%02d",e);
+            out += eb;
+        }
     }
 
     static Json makeArrayOfInts(const uint64_t *v, size_t n)

@@ -49,6 +49,13 @@ int ffr_flame_layout(const ffr_flame_desc *desc, double mult_d[FFR_MAX_DIMS],
 const char *ffr_var_name(uint32_t op);
 uint32_t ffr_var_op_from_name(const char *name);
 
+/* The flame as `std::cerr << "flame: " << json_flame` echoes it (ffr_buf.cpp:129 through
+   utils/json.cpp:203-207, i.e. nlohmann's compact dump: keys sorted, no whitespace, comments
+   gone). Writes at most outlen-1 characters + NUL into out (may be NULL) and returns the full
+   length; 0 and a message in err when the text does not parse. */
+size_t ffr_flame_json_echo(const char *text, size_t len, char *out, size_t outlen,
+        char *err, size_t errlen);
+
 /* ffr-buf's batch-size heuristic (ffr_buf.cpp:94-101): clamp((samples+255)>>8, 4096, 1<<20) */
 uint64_t ffr_reference_batch_size(uint64_t samples);
 

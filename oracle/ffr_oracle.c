@@ -1670,9 +1670,11 @@ int oracle_iterate_points(const ffr_flame_desc *fl, int64_t xf_index, u64 n, con
 /* ---------------- tone map ----------------
    Restates render_image (src/ffr_img.cpp:199-309) + ImageRenderer::getValueBounds /
    renderGrayImage / renderColorImageRGB (renderers/image_renderer.hpp:112-192) for one pixel
-   format. PARITY UNPINNED for this function: ffr-img cannot be built here (boost::gil and
-   libpng headers are absent), so there is no reference output to pin it to; the arithmetic is
-   a dozen lines and is restated literally. mode: 1 mono, 2 gray, 3 rgb; bits 8 or 16; out is
+   format. PINNED: ffr-img cannot be built here as a program (Boost and libpng are absent),
+   but its pixel arithmetic is compiled from the reference's own sources by
+   oracle/ref_img_harness.cpp (`make -C oracle refimg`); this function is bit-identical to it
+   for every mode x bit depth x gamma (tests/golden/golden_img.json, tests/test_golden.py,
+   tests/test_oracle_vs_reference.py). mode: 1 mono, 2 gray, 3 rgb; bits 8 or 16; out is
    u8 or u16 samples, channels interleaved. Returns 0, or -1 "histogram is (probably) empty".
    The double -> pixel casts of NaN (rgb, count 0: 0/0) and of 2^bits are undefined in the
    reference; as on the device they yield 0 and the top code. */

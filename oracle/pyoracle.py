@@ -3,6 +3,8 @@
 ctypes access to the two CPU checkers:
   libffr_oracle.so        our plain C restatement (oracle/ffr_oracle.c)
   _ref/libffr_ref.so      the unmodified reference behind oracle/ref_harness.cpp
+  _ref/libffr_refimg.so   the reference's tone map (image_renderer.hpp + render_image() of
+                          ffr_img.cpp) and its `os << Json` echo, behind ref_img_harness.cpp
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm import
 this module. Nothing here touches /root/reference at run time: _ref/libffr_ref.so is
 prebuilt by `make -C oracle ref` in the build container and travels with the repo.
@@ -20,6 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_LIB = os.path.join(_HERE, "libffr_oracle.so")
 REF_LIB = os.path.join(_HERE, "_ref", "libffr_ref.so")
 REF_LIB_F32 = os.path.join(_HERE, "_ref", "libffr_ref_f32.so")  # float/uint32_t configuration
+REFIMG_LIB = os.path.join(_HERE, "_ref", "libffr_refimg.so")    # tone map + "flame:" echo (ref_img_harness.cpp)
 
 ffr = importlib.import_module("flame-fractal-renderer_b200")
 
@@ -246,3 +249,54 @@ def ref_iterate_points(text, xf_index, seeds, pts, elem_size=8):
                                                seeds.ctypes.data_as(_u64p), pts.ctypes.data_as(_f64p),
                                                out.ctypes.data_as(_f64p)), elem_size)
     return out
+
+
+_refimg = None
+
+
+def have_refimg():
+    return os.path.exists(REFIMG_LIB)
+
+
+def refimg():
+    global _refimg
+    if _refimg is None:
+        l = C.CDLL(REFIMG_LIB)
+        l.refimg_last_error.restype = C.c_char_p
+        l.refimg_render.restype = C.c_int
+        l.refimg_render.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_double,
+                                    C.c_void_p, C.c_size_t, _u64p, _f64p]
+        l.refimg_flame_echo.restype = C.c_size_t
+        l.refimg_flame_echo.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+        _refimg = l
+    return _refimg
+
+
+def ref_tonemap(text, raw, mode, bits=8, gamma=1.0):
+    """The reference's own render_image() (ffr_img.cpp:199-309 over image_renderer.hpp) on a raw
+    double/u64 buffer: returns (image, info) like oracle_tonemap."""
+    fl = ffr.Flame(text)
+    w, h = fl.size[0], fl.size[1]
+    raw = np.ascontiguousarray(raw).view(np.uint64)
+    ch = 3 if mode == 3 else 1
+    if mode == 1:
+        bits = 8
+    img = np.zeros((h, w, ch), dtype=np.uint8 if bits == 8 else np.uint16)
+    hb = (C.c_uint64 * 2)()
+    lb = (C.c_double * 2)()
+    rc = refimg().refimg_render(_enc(text), raw.ctypes.data_as(C.c_void_p), raw.nbytes, mode, bits,
+                                gamma, img.ctypes.data_as(C.c_void_p), img.nbytes, hb, lb)
+    if rc:
+        raise RuntimeError("reference: " + refimg().refimg_last_error().decode())
+    info = {"hist_min": hb[0], "hist_max": hb[1], "scaler_min_printed": lb[0],
+            "scaler_max_printed": lb[1]}
+    return (img[:, :, 0] if ch == 1 else img), info
+
+
+def ref_flame_echo(text):
+    n = refimg().refimg_flame_echo(_enc(text), None, 0)
+    if not n:
+        raise RuntimeError("reference: " + refimg().refimg_last_error().decode())
+    out = C.create_string_buffer(n + 1)
+    refimg().refimg_flame_echo(_enc(text), out, n + 1)
+    return out.value.decode()

@@ -100,8 +100,47 @@ def test_threaded_oracle_counts_are_exact(ffr, po, examples):
         assert sa[k] == sb[k]
 
 
+with open(os.path.join(HERE, "golden", "golden_img.json")) as f:
+    GOLD_IMG = json.load(f)
+
+
+@pytest.mark.parametrize("name", sorted(GOLD_IMG["tonemap"]))
+def test_oracle_tonemap_matches_reference_pixels(ffr, po, examples, name):
+    """f1 pin: oracle_tonemap against the pixels the reference's own render_image()
+    (ffr_img.cpp:199-309 over image_renderer.hpp:112-192, compiled by `make -C oracle refimg`)
+    produced for the same seeded buffer -- every mode x bit depth x gamma, bit for bit."""
+    gold = GOLD_IMG["tonemap"][name]
+    pp = GOLD_IMG["params"]
+    fl = ffr.Flame(examples.example_json(name, size=gold["size"]))
+    po.set_nan_emulation(True)
+    try:
+        raw, _, _ = po.oracle_render(fl, pp["chains"], pp["chain_len"], base_seed=pp["base_seed"])
+    finally:
+        po.set_nan_emulation(False)
+    assert hashlib.sha256(raw.tobytes()).hexdigest() == gold["buffer_sha256"]
+    w, h = gold["size"]
+    for key, want in gold["cases"].items():
+        mode, bits, gamma = key.split("/")
+        img, info = po.oracle_tonemap(raw, w, h, fl.color_dims, int(mode), bits=int(bits),
+                                      gamma=float(gamma))
+        assert hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() == want["sha256"], key
+        assert info["hist_min"] == want["hist_min"] and info["hist_max"] == want["hist_max"]
+
+
+def test_flame_echo_matches_reference(ffr):
+    """The `flame: ...` line of ffr_buf.cpp:129 (nlohmann's compact dump through
+    utils/json.cpp:203-207): ffr_flame_json_echo against the text the reference printed."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden_img
+    texts = make_golden_img.echo_texts()
+    assert sorted(texts) == sorted(GOLD_IMG["echo"])
+    for key, text in texts.items():
+        assert ffr.flame_json_echo(text) == GOLD_IMG["echo"][key], key
+
+
 def test_oracle_tonemap_properties(ffr, po, examples):
-    """ffr-img pixel math (oracle restatement; unpinned, see ffr_oracle.c): exact identities
+    """ffr-img pixel math (oracle restatement, pinned above): exact identities
     that follow from src/ffr_img.cpp:236-243 -- the brightest cell is the top code, empty cells
     are 0, gamma 1 grey equals floor(log(1+n)/log(1+max) * 256(1-2^-52)), output is monotone
     in the count."""

@@ -1,7 +1,11 @@
 """f1: the log-density tone map (ffr-img's pixel math, src/ffr_img.cpp:199-309) on the device
-against the oracle restatement. Tolerance: log/pow are libm vs CUDA (1-2 ULP), so a pixel may
-differ by one code when v*scale falls within ~1e-13 of an integer: at most 1 code, on at most
-0.01 % of the pixels; mono mode and the histogram bounds are exact."""
+against (a) the reference's own code -- render_image() of ffr_img.cpp over
+renderers/image_renderer.hpp, compiled by `make -C oracle refimg` into
+oracle/_ref/libffr_refimg.so, which travels to the GPU box -- and (b) the oracle restatement,
+which tests/test_golden.py and tests/test_oracle_vs_reference.py show to be bit-identical to (a).
+Tolerance: log/pow are libm vs CUDA (1-2 ULP), so a pixel may differ by one code when v*scale
+falls within ~1e-13 of an integer: at most 1 code, on at most 0.01 % of the pixels; mono mode
+and the histogram bounds are exact."""
 import io
 import os
 import subprocess
@@ -62,6 +66,32 @@ def test_rgb(ffr, po, examples, bits):
     r.close()
     assert img.shape == (180, 320, 3)
     close_enough(img, want)
+
+
+@pytest.mark.parametrize("name,size,cd", [("tkoz_test3", [320, 180], 3),
+                                          ("csci6360_project", [256, 144], 0)])
+def test_against_reference_compiled_tonemap(ffr, po, examples, name, size, cd):
+    """Every mode x bit depth x gamma against the reference's own render_image()."""
+    if not po.have_refimg():
+        pytest.skip("oracle/_ref/libffr_refimg.so not built")
+    text = examples.example_json(name, size=size)
+    fl, r = rendered(ffr, examples, name, size)
+    raw = r.read_buffer()
+    n = 0
+    for mode in ((ffr.TONE_MONO, ffr.TONE_GRAY, ffr.TONE_RGB) if cd == 3 else (ffr.TONE_MONO, ffr.TONE_GRAY)):
+        for bits in (8, 16):
+            for gamma in (1.0, 2.2, 0.5, 4.0):
+                img, info = r.tonemap(mode, bits=bits, gamma=gamma)
+                want, winfo = po.ref_tonemap(text, raw, mode, bits, gamma)
+                assert img.shape == want.shape and img.dtype == want.dtype
+                assert info["hist_min"] == winfo["hist_min"] and info["hist_max"] == winfo["hist_max"]
+                if mode == ffr.TONE_MONO:
+                    assert np.array_equal(img, want)
+                else:
+                    close_enough(img, want)
+                n += 1
+    r.close()
+    assert n == (24 if cd == 3 else 16)
 
 
 def test_errors(ffr, examples):

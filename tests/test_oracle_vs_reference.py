@@ -86,3 +86,40 @@ def test_float_build_flatten_matches_float_reference(ffr, po, examples):
             assert all(float(np.float32(v)) == v for v in vals)
     # ISAAC-32 known answers of the float build
     assert list(po.ref_isaac_words(1, 4, elem_size=4)) == [676671429, 3101584658, 2918577689, 525991190]
+
+
+@pytest.mark.skipif(not pyoracle.have_refimg(), reason="oracle/_ref/libffr_refimg.so not built")
+@pytest.mark.parametrize("name,size", [("tkoz_test3", [200, 120]), ("tkoz_test1", [128, 96]),
+                                       ("sierpinski_triangle", [64, 64])])
+def test_tonemap_restatement_equals_reference_code(ffr, po, examples, name, size):
+    """f1: oracle_tonemap vs the reference's own render_image() + image_renderer.hpp compiled by
+    `make -C oracle refimg`, on other flames, seeds and gammas than the golden fixture."""
+    text = examples.example_json(name, size=size)
+    fl = ffr.Flame(text)
+    raw, _, _ = po.oracle_render(fl, 500, 800, base_seed=41, nthreads=8)
+    cd = fl.color_dims
+    for mode in (1, 2, 3):
+        if mode == 3 and cd != 3:
+            with pytest.raises(RuntimeError, match="buffer must use 3 color dimensions"):
+                po.ref_tonemap(text, raw, 3)
+            continue
+        for bits in (8, 16):
+            for gamma in (1.0, 1.7, 2.2, 0.3, 1e-3):
+                a, ia = po.ref_tonemap(text, raw, mode, bits, gamma)
+                b, ib = po.oracle_tonemap(raw, size[0], size[1], cd, mode, bits=bits, gamma=gamma)
+                assert np.array_equal(a, b), (mode, bits, gamma)
+                assert ia["hist_min"] == ib["hist_min"] and ia["hist_max"] == ib["hist_max"]
+    empty = np.zeros_like(raw)
+    with pytest.raises(RuntimeError, match="probably. empty"):
+        po.ref_tonemap(text, empty, 2)
+    with pytest.raises(RuntimeError, match="gamma too small"):
+        po.ref_tonemap(text, raw, 2, 8, 0.0)
+
+
+@pytest.mark.skipif(not pyoracle.have_refimg(), reason="oracle/_ref/libffr_refimg.so not built")
+def test_flame_echo_equals_reference_operator(ffr, po, examples):
+    texts = [examples.example_json(n) for n in examples.EXAMPLES]
+    texts += [flames.variation_flame(v, dims=d, final=True) for v in flames.ALL_VARIATIONS for d in (2, 3)]
+    texts += [flames.many_xforms_flame(), flames.one_d_flame(), flames.divergent_flame()]
+    for text in texts:
+        assert ffr.flame_json_echo(text) == po.ref_flame_echo(text)
