@@ -263,7 +263,7 @@ def main():
         rend.render_chains_async(first, chains_per_step, L, base_seed=1)
 
     def reduce_to_rank0():
-        sharding.reduce_buffer(buf, cells, cell, dst=0)
+        sharding.reduce_buffer(buf, cells, cell, dst=0, renderer=rend)
 
     # ---- warm-up (>= 3 steps); the clock sampler starts here, reports the timed region only ----
     sampler = ClockSampler(local_rank)
@@ -342,7 +342,7 @@ def main():
                 e2e_rend.add_buffer(in_np)
             first = sharding.step_chain_range(k + 500_000, rank, world, chains_per_step)
             e2e_rend.render_chains(first, chains_per_step, L, base_seed=1)
-            sharding.reduce_buffer(ebuf, cells, cell, dst=0)
+            sharding.reduce_buffer(ebuf, cells, cell, dst=0, renderer=e2e_rend)
             if rank == 0:
                 e2e_rend.read_buffer(out_np)
     else:

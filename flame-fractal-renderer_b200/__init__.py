@@ -159,6 +159,8 @@ ABI = {
     "ffr_cuda_resident_chains": (C.c_uint64, [C.c_void_p]),
     "ffr_cuda_launch_count": (C.c_uint64, [C.c_void_p]),
     "ffr_cuda_reduce": (C.c_int, [C.c_void_p]),
+    "ffr_cuda_sum_device_slices": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int,
+                                             C.c_uint64, C.c_uint64]),
     "ffr_cuda_read_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ffr_cuda_histogram_sum_max": (C.c_int, [C.c_void_p, _u64p, _u64p]),
     "ffr_cuda_tonemap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_size_t,
@@ -319,6 +321,7 @@ class BufferRenderer:
         self.elem_size = flame.elem_size
         self.word_dtype = np.uint64 if self.elem_size == 8 else np.uint32
         self.cell_size = 1 + flame.color_dims
+        self.own_stream = stream is None
         self._stats = FfrStats()
 
     def close(self):
@@ -381,6 +384,12 @@ class BufferRenderer:
 
     def reduce(self):
         self._check(lib().ffr_cuda_reduce(self._h))
+
+    def sum_device_slices(self, dst_ptr, src_ptrs, first_elem, n_elems):
+        """dst += sum(srcs) on the device, typed by position in the cell (K2d)."""
+        arr = (C.c_void_p * len(src_ptrs))(*src_ptrs)
+        self._check(lib().ffr_cuda_sum_device_slices(self._h, dst_ptr, arr, len(src_ptrs),
+                                                     first_elem, n_elems))
 
     @property
     def jit_info(self):

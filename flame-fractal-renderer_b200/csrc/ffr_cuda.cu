@@ -171,7 +171,7 @@ struct ffr_ctx
     size_t smem_bytes = 0;
     u64 launches = 0;
     std::string err;
-    bool peer_enabled = false;
+    bool peer_enabled = false, peer_probed = false;
     /* K1c, the run-time compiled flame-specialised kernel (ffr_jit_kernel.cuh) */
     uint32_t jit_mode = 0;         /* 0 auto (lazy, large renders), 1 off, 2 on at create */
     bool jit_eligible = false, jit_ready = false, jit_failed = false, jit_cached = false;
@@ -201,6 +201,28 @@ bool cuda_ok(ffr_ctx *ctx, cudaError_t e, const char *what)
 }
 
 #define CK(call) do { if (!cuda_ok(ctx,(call),#call)) return FFR_E_CUDA; } while (0)
+
+/* device temporaries of one ABI call: freed on every return path */
+struct DevTemp
+{
+    void *p = nullptr;
+    DevTemp() {}
+    DevTemp(const DevTemp&) = delete;
+    DevTemp &operator=(const DevTemp&) = delete;
+    ~DevTemp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p,bytes); }
+    template <typename U> U *as() const { return (U*)p; }
+};
+
+struct EventPair
+{
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~EventPair()
+    {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
 
 template <typename T, int D, int RCAP>
 render_fn pick_affine(bool affine_only)
@@ -796,6 +818,39 @@ void jit_maybe(ffr_ctx *ctx, u64 samples)
     }
 }
 
+/* K2b / K2c: what a K1e launch (or the attractor replay) left in its accumulation tile goes into
+   the buffer in the reference's cell order; the tile is all zero afterwards */
+int fold_tiles(ffr_ctx *ctx, DeviceState &ds)
+{
+    if (!ctx->jit_ready || !ds.d_acc)
+        return FFR_OK;
+    if (ds.d_dir)
+    {
+        /* K2c: the compact tile's rows into the buffer */
+        const u64 rows = ctx->cells >> FFR_DIR_ROW_SHIFT;
+        const unsigned fgrid = (unsigned)std::min<u64>((rows + 7)/8,(u64)ds.sm_count*16);
+        if (ctx->elem == 8)
+            fold_dir_kernel<u64><<<fgrid,256,0,ds.stream>>>((u64*)ds.d_acc,(u64*)ds.buffer,ds.d_dir,rows);
+        else
+            fold_dir_kernel<unsigned int><<<fgrid,256,0,ds.stream>>>((unsigned int*)ds.d_acc,(unsigned int*)ds.buffer,ds.d_dir,rows);
+    }
+    else
+    {
+        /* K2b: the launch's scrambled tile into the buffer (reference cell order) */
+        uint32_t inv = ctx->jit_cfg.acc_mul;      /* Newton: x <- x*(2 - m*x) doubles the valid bits */
+        for (int i = 0; i < 5; ++i)
+            inv *= 2u - ctx->jit_cfg.acc_mul*inv;
+        const unsigned fgrid = (unsigned)std::min<u64>((ctx->cells + 255)/256,(u64)ds.sm_count*16);
+        if (ctx->elem == 8)
+            fold_acc_kernel<u64><<<fgrid,256,0,ds.stream>>>((u64*)ds.d_acc,(u64*)ds.buffer,ctx->cells,inv,ctx->jit_cfg.acc_gran);
+        else
+            fold_acc_kernel<unsigned int><<<fgrid,256,0,ds.stream>>>((unsigned int*)ds.d_acc,(unsigned int*)ds.buffer,ctx->cells,inv,ctx->jit_cfg.acc_gran);
+    }
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    return FFR_OK;
+}
+
 int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_count, u64 chain_len,
         u64 last_len, u64 base_seed, u64 bv_limit)
 {
@@ -860,29 +915,11 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
             ctx->err = "cuLaunchKernel(ffr_jit_render): " + jit::cu_err(a,r);
             return FFR_E_CUDA;
         }
-        if (ds.d_dir && fn == ds.jmod.fn)
+        if (fn == ds.jmod.fn)
         {
-            /* K2c: the compact tile's rows into the buffer */
-            const u64 rows = ctx->cells >> FFR_DIR_ROW_SHIFT;
-            const unsigned fgrid = (unsigned)std::min<u64>((rows + 7)/8,(u64)ds.sm_count*16);
-            if (ctx->elem == 8)
-                fold_dir_kernel<u64><<<fgrid,256,0,ds.stream>>>((u64*)ds.d_acc,(u64*)ds.buffer,ds.d_dir,rows);
-            else
-                fold_dir_kernel<unsigned int><<<fgrid,256,0,ds.stream>>>((unsigned int*)ds.d_acc,(unsigned int*)ds.buffer,ds.d_dir,rows);
-            ++ctx->launches;
-        }
-        else if (ds.d_acc && fn == ds.jmod.fn)
-        {
-            /* K2b: the launch's scrambled tile into the buffer (reference cell order) */
-            uint32_t inv = ctx->jit_cfg.acc_mul;      /* Newton: x <- x*(2 - m*x) doubles the valid bits */
-            for (int i = 0; i < 5; ++i)
-                inv *= 2u - ctx->jit_cfg.acc_mul*inv;
-            const unsigned fgrid = (unsigned)std::min<u64>((ctx->cells + 255)/256,(u64)ds.sm_count*16);
-            if (ctx->elem == 8)
-                fold_acc_kernel<u64><<<fgrid,256,0,ds.stream>>>((u64*)ds.d_acc,(u64*)ds.buffer,ctx->cells,inv,ctx->jit_cfg.acc_gran);
-            else
-                fold_acc_kernel<unsigned int><<<fgrid,256,0,ds.stream>>>((unsigned int*)ds.d_acc,(unsigned int*)ds.buffer,ctx->cells,inv,ctx->jit_cfg.acc_gran);
-            ++ctx->launches;
+            const int frc = fold_tiles(ctx,ds);
+            if (frc != FFR_OK)
+                return frc;
         }
     }
     else
@@ -1020,7 +1057,12 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
     if (avail < 1)
         return fail("ffr_cuda_create(): no CUDA device available; libffr_cuda has no CPU fallback");
     ctx->scatter_mode = ctx->opt.scatter_mode;
-    if (ctx->scatter_mode == FFR_SCATTER_AUTO || ctx->scatter_mode == FFR_SCATTER_SMEM_TILE)
+    if (ctx->scatter_mode == FFR_SCATTER_SMEM_TILE)
+        return fail("ffr_cuda_create(): FFR_SCATTER_SMEM_TILE is not implemented (the shared memory of an SM "
+                    "holds the chains' ISAAC state; see DESIGN.md, scatter strategies)");
+    if (ctx->scatter_mode > FFR_SCATTER_TRACE)
+        return fail("ffr_cuda_create(): unknown scatter mode");
+    if (ctx->scatter_mode == FFR_SCATTER_AUTO)
         ctx->scatter_mode = FFR_SCATTER_GLOBAL;
     ctx->kernel = f32 ? pick_kernel<float>(ctx->dims,ctx->r,ctx->affine_only)
                       : pick_kernel<double>(ctx->dims,ctx->r,ctx->affine_only);
@@ -1356,61 +1398,185 @@ int ffr_cuda_render(ffr_ctx *ctx, uint64_t samples, uint64_t chain_len, uint64_t
     return FFR_OK;
 }
 
+/* launch K2d on `ds` for elements [first, first + n) of the buffer */
+static int launch_reduce_slices(ffr_ctx *ctx, DeviceState &ds, void *dst, const PeerSlices &ps, int n_src,
+        u64 first, u64 n)
+{
+    if (n == 0 || n_src == 0)
+        return FFR_OK;
+    const unsigned grid = (unsigned)std::min<u64>((n + 255)/256,(u64)ds.sm_count*8);
+    if (ctx->elem == 8)
+        reduce_slices_kernel<double><<<grid,256,0,ds.stream>>>((u64*)dst,ps,n_src,first,n,ctx->cellsz);
+    else
+        reduce_slices_kernel<float><<<grid,256,0,ds.stream>>>((unsigned int*)dst,ps,n_src,first,n,ctx->cellsz);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    return FFR_OK;
+}
+
 int ffr_cuda_reduce(ffr_ctx *ctx)
 {
     if (!ctx)
         return FFR_E_INVALID;
-    if (ctx->devs.size() < 2)
+    const size_t nd = ctx->devs.size();
+    if (nd < 2)
         return FFR_OK;
-    DeviceState &d0 = ctx->devs[0];
+    bool any = false;
+    for (size_t i = 1; i < nd; ++i)
+        any |= ctx->devs[i].dirty;
+    if (!any)
+        return FFR_OK;
+    if (nd > FFR_MAX_PEERS + 1)
+    {
+        ctx->err = "ffr_cuda_reduce(): at most 16 devices";
+        return FFR_E_INVALID;
+    }
     int rc = sync_all(ctx);
     if (rc != FFR_OK)
         return rc;
-    const size_t n_elems = ctx->bytes/ctx->elem;
-    for (size_t i = 1; i < ctx->devs.size(); ++i)
+    /* peer access between every pair, decided once per context */
+    if (!ctx->peer_probed)
+    {
+        ctx->peer_probed = true;
+        ctx->peer_enabled = true;
+        for (size_t i = 0; i < nd && ctx->peer_enabled; ++i)
+            for (size_t j = 0; j < nd; ++j)
+            {
+                if (i == j)
+                    continue;
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can,ctx->devs[i].dev,ctx->devs[j].dev));
+                if (!can)
+                {
+                    ctx->peer_enabled = false;
+                    break;
+                }
+            }
+        if (ctx->peer_enabled)
+            for (size_t i = 0; i < nd; ++i)
+            {
+                CK(cudaSetDevice(ctx->devs[i].dev));
+                for (size_t j = 0; j < nd; ++j)
+                {
+                    if (i == j)
+                        continue;
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(ctx->devs[j].dev,0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled)
+                        cudaGetLastError();
+                    else
+                        CK(e);
+                }
+            }
+    }
+    DeviceState &d0 = ctx->devs[0];
+    const u64 n_elems = ctx->bytes/ctx->elem;
+    if (!ctx->peer_enabled)
+    {
+        /* no P2P path between some pair: device 0 adds one staged copy after the other (the
+           staging buffer is the one add_buffer keeps) */
+        CK(cudaSetDevice(d0.dev));
+        const u64 chunk = std::min<u64>(n_elems,((u64)1 << 27)/ctx->elem);
+        if (d0.stage_elems < chunk)
+        {
+            if (d0.d_stage)
+                cudaFree(d0.d_stage);
+            d0.d_stage = nullptr;
+            d0.stage_elems = 0;
+            CK(cudaMalloc(&d0.d_stage,chunk*ctx->elem));
+            d0.stage_elems = chunk;
+        }
+        for (size_t i = 1; i < nd; ++i)
+        {
+            if (!ctx->devs[i].dirty)
+                continue;
+            for (u64 off = 0; off < n_elems; off += chunk)
+            {
+                const u64 n = std::min<u64>(chunk,n_elems - off);
+                CK(cudaMemcpyPeerAsync(d0.d_stage,d0.dev,(const char*)ctx->devs[i].buffer + off*ctx->elem,
+                    ctx->devs[i].dev,n*ctx->elem,d0.stream));
+                PeerSlices ps;
+                memset(&ps,0,sizeof(ps));
+                ps.src[0] = d0.d_stage;
+                rc = launch_reduce_slices(ctx,d0,(char*)d0.buffer + off*ctx->elem,ps,1,off,n);
+                if (rc != FFR_OK)
+                    return rc;
+            }
+        }
+        CK(cudaStreamSynchronize(d0.stream));
+    }
+    else
+    {
+        /* reduce-scatter: device d sums slice d of every private buffer into its own, all devices
+           at once; then device 0 gathers the finished slices. Slices are whole cells. */
+        const u64 cells_per = (ctx->cells + nd - 1)/nd;
+        std::vector<cudaEvent_t> done(nd,nullptr);
+        struct EvGuard
+        {
+            std::vector<cudaEvent_t> &v;
+            ~EvGuard() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+        } guard{done};
+        for (size_t d = 0; d < nd; ++d)
+        {
+            DeviceState &ds = ctx->devs[d];
+            CK(cudaSetDevice(ds.dev));
+            const u64 c0 = std::min<u64>(cells_per*d,ctx->cells), c1 = std::min<u64>(c0 + cells_per,ctx->cells);
+            const u64 first = c0*ctx->cellsz, n = (c1 - c0)*ctx->cellsz;
+            PeerSlices ps;
+            memset(&ps,0,sizeof(ps));
+            int k = 0;
+            for (size_t j = 0; j < nd; ++j)
+                if (j != d && (ctx->devs[j].dirty || j == 0))
+                    ps.src[k++] = (const char*)ctx->devs[j].buffer + first*ctx->elem;
+            rc = launch_reduce_slices(ctx,ds,(char*)ds.buffer + first*ctx->elem,ps,k,first,n);
+            if (rc != FFR_OK)
+                return rc;
+            CK(cudaEventCreateWithFlags(&done[d],cudaEventDisableTiming));
+            CK(cudaEventRecord(done[d],ds.stream));
+        }
+        CK(cudaSetDevice(d0.dev));
+        for (size_t d = 1; d < nd; ++d)
+        {
+            const u64 c0 = std::min<u64>(cells_per*d,ctx->cells), c1 = std::min<u64>(c0 + cells_per,ctx->cells);
+            const u64 first = c0*ctx->cellsz, n = (c1 - c0)*ctx->cellsz;
+            if (n == 0)
+                continue;
+            CK(cudaStreamWaitEvent(d0.stream,done[d],0));
+            CK(cudaMemcpyPeerAsync((char*)d0.buffer + first*ctx->elem,d0.dev,
+                (const char*)ctx->devs[d].buffer + first*ctx->elem,ctx->devs[d].dev,n*ctx->elem,d0.stream));
+        }
+        /* every device must be done reading device 0's slices before anything else touches them */
+        for (size_t d = 1; d < nd; ++d)
+            CK(cudaStreamWaitEvent(d0.stream,done[d],0));
+        CK(cudaStreamSynchronize(d0.stream));
+    }
+    /* the peers' samples now live in device 0: clear them so a later reduce adds nothing twice */
+    for (size_t i = 1; i < nd; ++i)
     {
         DeviceState &ds = ctx->devs[i];
-        if (!ds.dirty)
-            continue;
-        CK(cudaSetDevice(d0.dev));
-        int can = 0;
-        CK(cudaDeviceCanAccessPeer(&can,d0.dev,ds.dev));
-        const void *src = ds.buffer;
-        void *staged = nullptr;
-        if (can)
-        {
-            cudaError_t e = cudaDeviceEnablePeerAccess(ds.dev,0);
-            if (e == cudaErrorPeerAccessAlreadyEnabled)
-                cudaGetLastError();
-            else
-                CK(e);
-        }
-        else
-        {
-            /* no NVLink/P2P path between the two: stage through a copy */
-            CK(cudaMalloc(&staged,ctx->bytes));
-            CK(cudaMemcpyPeerAsync(staged,d0.dev,ds.buffer,ds.dev,ctx->bytes,d0.stream));
-            src = staged;
-        }
-        /* device 0 pulls the peer's buffer over NVLink and adds it, typed by position */
-        unsigned grid = (unsigned)std::min<size_t>((n_elems + 255)/256,(size_t)d0.sm_count*16);
-        if (ctx->elem == 8)
-            add_buffer_kernel<double><<<grid,256,0,d0.stream>>>((u64*)d0.buffer,(const u64*)src,n_elems,ctx->cellsz);
-        else
-            add_buffer_kernel<float><<<grid,256,0,d0.stream>>>((unsigned int*)d0.buffer,
-                (const unsigned int*)src,n_elems,ctx->cellsz);
-        ++ctx->launches;
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(d0.stream));
-        if (staged)
-            cudaFree(staged);
-        /* the peer's samples now live in device 0: clear it so a later reduce adds nothing twice */
         CK(cudaSetDevice(ds.dev));
         CK(cudaMemsetAsync(ds.buffer,0,ctx->bytes,ds.stream));
-        CK(cudaStreamSynchronize(ds.stream));
         ds.dirty = false;
     }
-    return FFR_OK;
+    return sync_all(ctx);
+}
+
+int ffr_cuda_sum_device_slices(ffr_ctx *ctx, void *dst, const void *const *srcs, int n_src,
+        uint64_t first_elem, uint64_t n_elems)
+{
+    if (!ctx || !dst || !srcs || n_src < 0 || n_src > FFR_MAX_PEERS)
+        return FFR_E_INVALID;
+    if (ctx->devs.size() != 1)
+    {
+        ctx->err = "sum_device_slices needs a single device context";
+        return FFR_E_INVALID;
+    }
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    PeerSlices ps;
+    memset(&ps,0,sizeof(ps));
+    for (int k = 0; k < n_src; ++k)
+        ps.src[k] = srcs[k];
+    return launch_reduce_slices(ctx,ds,dst,ps,n_src,first_elem,n_elems);
 }
 
 int ffr_cuda_read_buffer(ffr_ctx *ctx, void *host, size_t bytes)
@@ -1534,8 +1700,9 @@ int ffr_cuda_tonemap(ffr_ctx *ctx, int mode, int bits, double gamma, void *pixel
         ctx->err = "histogram is (probably) empty";
         return FFR_E_INVALID;
     }
-    void *d_pix = nullptr;
-    CK(cudaMalloc(&d_pix,need));
+    DevTemp pix;
+    CK(pix.alloc(need));
+    void *d_pix = pix.p;
     /* num_t gp = 1.0 / arg_gamma (:235); arg_gamma is a num_t */
     if (ctx->elem == 8)
     {
@@ -1558,14 +1725,9 @@ int ffr_cuda_tonemap(ffr_ctx *ctx, int mode, int bits, double gamma, void *pixel
                 ctx->cells,ctx->cellsz,mode,mm[1],gp,(unsigned short*)d_pix);
     }
     ++ctx->launches;
-    if (!cuda_ok(ctx,cudaGetLastError(),"tonemap_kernel") ||
-        !cuda_ok(ctx,cudaMemcpyAsync(pixels,d_pix,need,cudaMemcpyDeviceToHost,ds.stream),"tonemap D2H") ||
-        !cuda_ok(ctx,cudaStreamSynchronize(ds.stream),"tonemap sync"))
-    {
-        cudaFree(d_pix);
-        return FFR_E_CUDA;
-    }
-    cudaFree(d_pix);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(pixels,d_pix,need,cudaMemcpyDeviceToHost,ds.stream));
+    CK(cudaStreamSynchronize(ds.stream));
     return FFR_OK;
 }
 
@@ -1597,12 +1759,13 @@ int ffr_cuda_iterate_points(ffr_ctx *ctx, int64_t xf_index, uint64_t n, const ui
         return FFR_OK;
     DeviceState &ds = ctx->devs[0];
     CK(cudaSetDevice(ds.dev));
-    u64 *d_seeds = nullptr;
-    double *d_in = nullptr, *d_out = nullptr;
+    DevTemp t_seeds, t_in, t_out;
     const size_t pb = n*ctx->dims*sizeof(double);
-    CK(cudaMalloc(&d_seeds,n*8));
-    CK(cudaMalloc(&d_in,pb));
-    CK(cudaMalloc(&d_out,pb));
+    CK(t_seeds.alloc(n*8));
+    CK(t_in.alloc(pb));
+    CK(t_out.alloc(pb));
+    u64 *d_seeds = t_seeds.as<u64>();
+    double *d_in = t_in.as<double>(), *d_out = t_out.as<double>();
     CK(cudaMemcpyAsync(d_seeds,seeds,n*8,cudaMemcpyHostToDevice,ds.stream));
     CK(cudaMemcpyAsync(d_in,pts_in,pb,cudaMemcpyHostToDevice,ds.stream));
     const unsigned grid = (unsigned)((n + FFR_TPB - 1)/FFR_TPB);
@@ -1630,9 +1793,6 @@ int ffr_cuda_iterate_points(ffr_ctx *ctx, int64_t xf_index, uint64_t n, const ui
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(pts_out,d_out,pb,cudaMemcpyDeviceToHost,ds.stream));
     CK(cudaStreamSynchronize(ds.stream));
-    cudaFree(d_seeds);
-    cudaFree(d_in);
-    cudaFree(d_out);
     return FFR_OK;
 }
 
@@ -1644,8 +1804,9 @@ int ffr_cuda_isaac_words(ffr_ctx *ctx, uint64_t seed, uint64_t n, uint64_t *out)
         return FFR_OK;
     DeviceState &ds = ctx->devs[0];
     CK(cudaSetDevice(ds.dev));
-    u64 *d_out = nullptr;
-    CK(cudaMalloc(&d_out,n*8));
+    DevTemp t_out;
+    CK(t_out.alloc(n*8));
+    u64 *d_out = t_out.as<u64>();
     if (ctx->elem == 8)
     {
         CK(cudaFuncSetAttribute((const void*)isaac_words_kernel<double>,
@@ -1658,7 +1819,6 @@ int ffr_cuda_isaac_words(ffr_ctx *ctx, uint64_t seed, uint64_t n, uint64_t *out)
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out,d_out,n*8,cudaMemcpyDeviceToHost,ds.stream));
     CK(cudaStreamSynchronize(ds.stream));
-    cudaFree(d_out);
     return FFR_OK;
 }
 
@@ -1752,75 +1912,77 @@ int ffr_cuda_atomic_roofline_ex(ffr_ctx *ctx, uint64_t n_atomics, int pattern, f
     }
     DeviceState &ds = ctx->devs[0];
     CK(cudaSetDevice(ds.dev));
-    const u64 grid = (u64)ds.sm_count * ds.blocks_per_sm;
-    const u64 threads = grid*FFR_TPB;
-    const u64 per_thread = std::max<u64>(1,n_atomics/threads);
-    cudaEvent_t e0,e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    int rc = FFR_OK;
+    /* both microbenchmarks: every SM full (8 x 256 threads), REDs issued back to back */
+    const u64 grid = (u64)ds.sm_count * 8;
+    EventPair ev;
+    CK(cudaEventCreate(&ev.e0));
+    CK(cudaEventCreate(&ev.e1));
     if (pattern == 0)
     {
-        CK(cudaEventRecord(e0,ds.stream));
+        const u64 threads = grid*FFR_REPLAY_TPB;
+        const u64 per_thread = std::max<u64>(8,(n_atomics/threads) & ~7ULL);
+        CK(cudaEventRecord(ev.e0,ds.stream));
         if (ctx->elem == 8)
-            atomic_bench_kernel<double><<<(unsigned)grid,FFR_TPB,0,ds.stream>>>((u64*)ds.buffer,ctx->cells,
+            atomic_bench_kernel<double><<<(unsigned)grid,FFR_REPLAY_TPB,0,ds.stream>>>((u64*)ds.buffer,ctx->cells,
                 ctx->cellsz,per_thread,0x1234u + ctx->launches);
         else
-            atomic_bench_kernel<float><<<(unsigned)grid,FFR_TPB,0,ds.stream>>>((unsigned int*)ds.buffer,
+            atomic_bench_kernel<float><<<(unsigned)grid,FFR_REPLAY_TPB,0,ds.stream>>>((unsigned int*)ds.buffer,
                 ctx->cells,ctx->cellsz,per_thread,0x1234u + ctx->launches);
         ++ctx->launches;
         CK(cudaGetLastError());
-        CK(cudaEventRecord(e1,ds.stream));
-        CK(cudaEventSynchronize(e1));
-        CK(cudaEventElapsedTime(ms,e0,e1));
+        CK(cudaEventRecord(ev.e1,ds.stream));
+        CK(cudaEventSynchronize(ev.e1));
+        CK(cudaEventElapsedTime(ms,ev.e0,ev.e1));
         if (n_done)
             *n_done = per_thread*threads;
+        ds.dirty = true;
+        return FFR_OK;
     }
+    /* record: the chains the render kernel keeps resident, n_atomics/chains samples each (an even
+       number of chains: the replay reads entry pairs); statistics saved and restored */
+    u64 chains = std::max<u64>(2,ffr_cuda_resident_chains(ctx)) & ~1ULL;
+    const u64 per_chain = std::max<u64>(1,n_atomics/chains);
+    const u64 entries = chains*per_chain;
+    DevTemp trace, saved;
+    CK(trace.alloc(entries*sizeof(u64)));
+    CK(saved.alloc(sizeof(DevStats)));
+    CK(cudaMemsetAsync(trace.p,0xff,entries*sizeof(u64),ds.stream));
+    CK(cudaMemcpyAsync(saved.p,ds.d_stats,sizeof(DevStats),cudaMemcpyDeviceToDevice,ds.stream));
+    const uint32_t mode = ctx->scatter_mode;
+    ctx->scatter_mode = FFR_SCATTER_TRACE;
+    ds.d_trace = trace.as<u64>();
+    int rc = launch_render(ctx,ds,0x7ace0000ULL,chains,per_chain,0,1,~0ULL);
+    ctx->scatter_mode = mode;
+    ds.d_trace = nullptr;
+    if (rc != FFR_OK)
+        return rc;
+    DevStats after, before;
+    CK(cudaMemcpyAsync(&after,ds.d_stats,sizeof(DevStats),cudaMemcpyDeviceToHost,ds.stream));
+    CK(cudaMemcpyAsync(&before,saved.p,sizeof(DevStats),cudaMemcpyDeviceToHost,ds.stream));
+    CK(cudaStreamSynchronize(ds.stream));
+    if (n_done)
+        *n_done = after.s_plot - before.s_plot;
+    CK(cudaMemcpyAsync(ds.d_stats,saved.p,sizeof(DevStats),cudaMemcpyDeviceToDevice,ds.stream));
+    CK(cudaEventRecord(ev.e0,ds.stream));
+    if (ctx->elem == 8)
+        atomic_replay_kernel<double><<<(unsigned)grid,FFR_REPLAY_TPB,0,ds.stream>>>((u64*)ds.buffer,(u64*)ds.d_acc,
+            trace.as<ulonglong2>(),entries/2,ctx->cellsz);
     else
-    {
-        /* record: one full wave of chains, per_thread samples each, statistics saved/restored */
-        u64 *trace = nullptr;
-        DevStats *saved = nullptr;
-        CK(cudaMalloc(&trace,threads*per_thread*sizeof(u64)));
-        CK(cudaMalloc(&saved,sizeof(DevStats)));
-        CK(cudaMemsetAsync(trace,0xff,threads*per_thread*sizeof(u64),ds.stream));
-        CK(cudaMemcpyAsync(saved,ds.d_stats,sizeof(DevStats),cudaMemcpyDeviceToDevice,ds.stream));
-        const uint32_t mode = ctx->scatter_mode;
-        ctx->scatter_mode = FFR_SCATTER_TRACE;
-        ds.d_trace = trace;
-        rc = launch_render(ctx,ds,0x7ace0000ULL,threads,per_thread,0,1,~0ULL);
-        ctx->scatter_mode = mode;
-        ds.d_trace = nullptr;
-        if (rc == FFR_OK)
-        {
-            DevStats after;
-            CK(cudaMemcpyAsync(&after,ds.d_stats,sizeof(DevStats),cudaMemcpyDeviceToHost,ds.stream));
-            DevStats before;
-            CK(cudaMemcpyAsync(&before,saved,sizeof(DevStats),cudaMemcpyDeviceToHost,ds.stream));
-            CK(cudaStreamSynchronize(ds.stream));
-            if (n_done)
-                *n_done = after.s_plot - before.s_plot;
-            CK(cudaMemcpyAsync(ds.d_stats,saved,sizeof(DevStats),cudaMemcpyDeviceToDevice,ds.stream));
-            CK(cudaEventRecord(e0,ds.stream));
-            if (ctx->elem == 8)
-                atomic_replay_kernel<double><<<(unsigned)grid,FFR_TPB,0,ds.stream>>>((u64*)ds.buffer,trace,
-                    threads,per_thread,ctx->cellsz);
-            else
-                atomic_replay_kernel<float><<<(unsigned)grid,FFR_TPB,0,ds.stream>>>((unsigned int*)ds.buffer,
-                    trace,threads,per_thread,ctx->cellsz);
-            ++ctx->launches;
-            CK(cudaGetLastError());
-            CK(cudaEventRecord(e1,ds.stream));
-            CK(cudaEventSynchronize(e1));
-            CK(cudaEventElapsedTime(ms,e0,e1));
-        }
-        cudaFree(trace);
-        cudaFree(saved);
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+        atomic_replay_kernel<float><<<(unsigned)grid,FFR_REPLAY_TPB,0,ds.stream>>>((unsigned int*)ds.buffer,
+            (unsigned int*)ds.d_acc,trace.as<ulonglong2>(),entries/2,ctx->cellsz);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev.e1,ds.stream));
+    CK(cudaEventSynchronize(ev.e1));
+    CK(cudaEventElapsedTime(ms,ev.e0,ev.e1));
+    /* what the replay put into K1e's tile goes where a render's would: the tile stays all zero
+       between launches */
+    rc = fold_tiles(ctx,ds);
+    if (rc != FFR_OK)
+        return rc;
+    CK(cudaStreamSynchronize(ds.stream));
     ds.dirty = true;
-    return rc;
+    return FFR_OK;
 }
 
 } // extern "C"

@@ -338,9 +338,14 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
                     {
                         const JIDX bi = jaf_index(p); /* :202-209 */
                         W *cell = buffer + bi;
+#if defined(JACC_MUL) || defined(JDIR_CAP)
+                        /* the diagnostics scatter into the buffer itself; the trace records the
+                           address the render's scatter uses */
+                        const bool tiled = !MODES || trace != nullptr;
+#endif
 #ifdef JACC_MUL
                         /* the launch's own tile, cells in scrambled order (fold_acc_kernel) */
-                        if (!MODES)
+                        if (tiled)
                             cell = acc + ((((((unsigned)bi >> JACC_GRAN)*JACC_MUL) & JACC_MASK) << JACC_GRAN) |
                                           ((unsigned)bi & ((1u << JACC_GRAN) - 1u)));
 #endif
@@ -348,7 +353,7 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
                         /* compact tile: rows of 512 cells allocated on first touch (fold_dir_kernel).
                            The directory is read through L1: a stale line can only say "not allocated
                            yet", which sends the lane to the coherent slow path. */
-                        if (!MODES)
+                        if (tiled)
                         {
                             const unsigned row = (unsigned)(bi >> FFR_DIR_ROW_SHIFT);
                             unsigned slot = __ldca(&prm.dir[row]);
@@ -366,7 +371,15 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
                         else
                         {
                             if (trace)
-                                trace[(u64)it*prm.chain_count + kk] = bi;
+                            {
+#if defined(JACC_MUL) || defined(JDIR_CAP)
+                                const bool in_acc = cell >= acc && cell < acc + JACC_ELEMS;
+                                trace[(u64)it*prm.chain_count + kk] = in_acc ? ((1ULL << 63) | (u64)(cell - acc))
+                                                                             : (u64)(cell - buffer);
+#else
+                                trace[(u64)it*prm.chain_count + kk] = (u64)bi;
+#endif
+                            }
                             if (warp_agg)
                             {
                                 const unsigned pe = __match_any_sync(__activemask(),(u64)bi);

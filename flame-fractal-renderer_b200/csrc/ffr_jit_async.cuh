@@ -277,7 +277,8 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
         JIT_START_AND_PUSH(fresh,slot,key);
     }
 
-    unsigned long long spins = 0;
+    unsigned long long spins = 0;   /* idle polls since this BLOCK last made progress */
+    unsigned last_sig = 0;
 #ifdef JROT_STATIC
     /* warps that share a scheduler (warp index mod 4) prefer the same queues, so that its
        instruction cache holds fewer xform bodies */
@@ -338,6 +339,19 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
                 break;
             ++fails;
             __nanosleep(64);
+            /* Watchdog against a lost slot (a protocol bug), not against waiting: with fewer live
+               chains than threads -- a handful of very long chains, or the drain of a launch --
+               warps legitimately find nothing to pop for as long as the launch runs. The queue
+               heads move whenever ANY warp of the block pops, so only 2^24 consecutive polls
+               during which no head moved count as a stall. */
+            {
+                const unsigned sig = __reduce_add_sync(0xffffffffu,hd);
+                if (sig != last_sig)
+                {
+                    last_sig = sig;
+                    spins = 0;
+                }
+            }
             if (++spins > (1ULL << 24))
             {
                 if (lane == 0)
@@ -347,6 +361,7 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
         }
         if (q == JKEY_NONE)
             break;
+        spins = 0;      /* the watchdog measures one stall, not the idle time of a whole launch */
 
         const bool act = (unsigned)lane < n;
         unsigned slot = 0;

@@ -17,9 +17,11 @@ ahead-of-time kernels then serve every flame.
 #include <cuda.h>
 #include <nvrtc.h>
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <cerrno>
 #include <cmath>
 #include <cstdlib>
 #include <map>
@@ -664,9 +666,10 @@ std::string generate_affine(const std::vector<unsigned char> &blobv, const u64 *
           << "\n#define JTPB " << cfg.tpb << "\n#define JMINB " << cfg.minb << "\n#define JNPAIR " << npair << "\n";
         if (cfg.acc_mul)
             h << "#define JACC_MUL " << cfg.acc_mul << "u\n#define JACC_MASK " << ((fl->cells - 1) >> cfg.acc_gran)
-              << "u\n#define JACC_GRAN " << cfg.acc_gran << "\n";
+              << "u\n#define JACC_GRAN " << cfg.acc_gran << "\n#define JACC_ELEMS " << fl->cells << "ULL\n";
         if (cfg.dir_cap)
-            h << "#define JDIR_CAP " << cfg.dir_cap << "u\n";
+            h << "#define JDIR_CAP " << cfg.dir_cap << "u\n#define JACC_ELEMS "
+              << ((unsigned long long)cfg.dir_cap << FFR_DIR_ROW_SHIFT) << "ULL\n";
         h << "\n";
         o << "/* XForm::applyIteration for every xform of the flame; tb = coefficient table + xform index */\n";
         if (p_nz)
@@ -757,13 +760,74 @@ inline u64 fnv1a(const void *data, size_t n, u64 h = 0xcbf29ce484222325ULL)
     return h;
 }
 
+/* a second, independent 64-bit hash of the same bytes (multiply-xorshift over 8-byte words):
+   together with fnv1a the cache key is 128 bits, and both halves are stored INSIDE the entry */
+inline u64 mxhash(const void *data, size_t n, u64 h = 0x9e3779b97f4a7c15ULL)
+{
+    const unsigned char *p = (const unsigned char*)data;
+    while (n)
+    {
+        u64 w = 0;
+        const size_t k = n < 8 ? n : 8;
+        memcpy(&w,p,k);
+        p += k;
+        n -= k;
+        h = (h ^ w ^ ((u64)k << 56)) * 0xff51afd7ed558ccdULL;
+        h ^= h >> 32;
+        h *= 0xc4ceb9fe1a85ec53ULL;
+        h ^= h >> 29;
+    }
+    return h;
+}
+
+/* Where compiled kernels are kept between runs: FFR_JIT_CACHE, else $XDG_CACHE_HOME/ffr-b200-jit,
+   else ~/.cache/ffr-b200-jit -- never a shared, predictable path under /tmp. Empty: no disk cache. */
 inline std::string cache_dir()
 {
     const char *e = getenv("FFR_JIT_CACHE");
     if (e && *e)
         return e;
-    return "/tmp/ffr-b200-jit-" + std::to_string((unsigned)getuid());
+    e = getenv("XDG_CACHE_HOME");
+    if (e && *e == '/')
+        return std::string(e) + "/ffr-b200-jit";
+    e = getenv("HOME");
+    if (e && *e == '/')
+        return std::string(e) + "/.cache/ffr-b200-jit";
+    return std::string();
 }
+
+/* The directory is only used when it is a real directory (not a symlink) that belongs to this
+   user and that nobody else can write to or read: a cubin is code that runs in the caller's
+   CUDA context. Created 0700 (with its parent) on first use when `create` is set. */
+inline bool cache_dir_usable(const std::string &dir, bool create)
+{
+    if (dir.empty())
+        return false;
+    struct stat st;
+    if (lstat(dir.c_str(),&st) != 0)
+    {
+        if (!create)
+            return false;
+        const size_t cut = dir.find_last_of('/');
+        if (cut != std::string::npos && cut > 0)
+            mkdir(dir.substr(0,cut).c_str(),0700);     /* e.g. ~/.cache; fine if it exists */
+        if (mkdir(dir.c_str(),0700) != 0 && errno != EEXIST)
+            return false;
+        if (lstat(dir.c_str(),&st) != 0)
+            return false;
+    }
+    return S_ISDIR(st.st_mode) && st.st_uid == getuid() && (st.st_mode & 077) == 0;
+}
+
+/* cache entry = header | cubin | register spill bytes (8) */
+struct CacheHeader
+{
+    char magic[8];          /* "FFRJIT2\0" */
+    u64 key_fnv, key_mx;    /* the full 128-bit key again: a file under the wrong name is refused */
+    u64 key_bytes;          /* length of the hashed material (source + headers + compiler version) */
+    u64 payload_bytes;      /* cubin + 8 */
+    u64 payload_fnv;        /* truncated or damaged entries are refused */
+};
 
 struct Shim { const char *name; const char *text; size_t len; };
 
@@ -802,7 +866,7 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
         bool *from_cache, long *spill_bytes, bool cache_only = false)
 {
     /* the last 8 bytes of a cached entry hold the kernel's register spill bytes (ptxas -v) */
-    static std::map<u64,std::vector<char>> mem_cache;
+    static std::map<std::pair<u64,u64>,std::vector<char>> mem_cache;
     auto split = [&](std::vector<char> &blob)
     {
         long long sp = 0;
@@ -825,13 +889,21 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
     int vmaj = 0, vmin = 0;
     a.Version(&vmaj,&vmin);
     u64 h = fnv1a(src.data(),src.size());
+    u64 h2 = mxhash(src.data(),src.size());
+    u64 key_bytes = src.size();
     for (const Shim &s : headers())
+    {
         h = fnv1a(s.text,s.len,h);
+        h2 = mxhash(s.text,s.len,h2);
+        key_bytes += s.len;
+    }
     const int ver[2] = {vmaj,vmin};
     h = fnv1a(ver,sizeof(ver),h);
+    h2 = mxhash(ver,sizeof(ver),h2);
+    key_bytes += sizeof(ver);
     {
         std::lock_guard<std::mutex> lock(mu);
-        auto it = mem_cache.find(h);
+        auto it = mem_cache.find(std::make_pair(h,h2));
         if (it != mem_cache.end())
         {
             cubin = it->second;
@@ -841,28 +913,43 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
         }
     }
     char name[64];
-    snprintf(name,sizeof(name),"/%016llx.cubin",(unsigned long long)h);
+    snprintf(name,sizeof(name),"/%016llx%016llx.cubin",(unsigned long long)h,(unsigned long long)h2);
     const std::string dir = cache_dir();
     const std::string path = dir + name;
     const char *nocache = getenv("FFR_JIT_NO_DISK_CACHE");
-    if (!(nocache && *nocache == '1'))
+    const bool disk = !(nocache && *nocache == '1') && !dir.empty();
+    if (disk && cache_dir_usable(dir,false))
     {
-        if (FILE *f = fopen(path.c_str(),"rb"))
+        /* O_NOFOLLOW: an entry is a regular file of ours, never a link to somewhere else */
+        const int fd = open(path.c_str(),O_RDONLY | O_NOFOLLOW | O_CLOEXEC);
+        FILE *f = fd >= 0 ? fdopen(fd,"rb") : nullptr;
+        if (!f && fd >= 0)
+            close(fd);
+        if (f)
         {
-            fseek(f,0,SEEK_END);
-            long n = ftell(f);
-            fseek(f,0,SEEK_SET);
-            cubin.resize(n > 0 ? (size_t)n : 0);
-            const bool ok = n > 0 && fread(cubin.data(),1,(size_t)n,f) == (size_t)n;
+            CacheHeader hd;
+            struct stat st;
+            bool ok = fstat(fd,&st) == 0 && S_ISREG(st.st_mode) && st.st_uid == getuid() &&
+                fread(&hd,1,sizeof(hd),f) == sizeof(hd) && memcmp(hd.magic,"FFRJIT2",8) == 0 &&
+                hd.key_fnv == h && hd.key_mx == h2 && hd.key_bytes == key_bytes &&
+                hd.payload_bytes > 8 && hd.payload_bytes < (1ULL << 30) &&
+                (u64)st.st_size == sizeof(hd) + hd.payload_bytes;
+            if (ok)
+            {
+                cubin.resize((size_t)hd.payload_bytes);
+                ok = fread(cubin.data(),1,cubin.size(),f) == cubin.size() &&
+                    fnv1a(cubin.data(),cubin.size()) == hd.payload_fnv;
+            }
             fclose(f);
             if (ok)
             {
                 std::lock_guard<std::mutex> lock(mu);
-                mem_cache[h] = cubin;
+                mem_cache[std::make_pair(h,h2)] = cubin;
                 split(cubin);
                 if (from_cache) *from_cache = true;
                 return true;
             }
+            cubin.clear();
         }
     }
     if (cache_only)
@@ -958,20 +1045,32 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
     memcpy(entry.data() + cubin.size(),&spills,8);
     clock_gettime(CLOCK_MONOTONIC,&t1);
     if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9*(double)(t1.tv_nsec - t0.tv_nsec);
-    if (!(nocache && *nocache == '1'))
+    if (disk && cache_dir_usable(dir,true))
     {
-        mkdir(dir.c_str(),0700);
+        CacheHeader hd;
+        memset(&hd,0,sizeof(hd));
+        memcpy(hd.magic,"FFRJIT2",8);
+        hd.key_fnv = h;
+        hd.key_mx = h2;
+        hd.key_bytes = key_bytes;
+        hd.payload_bytes = entry.size();
+        hd.payload_fnv = fnv1a(entry.data(),entry.size());
         const std::string tmp = path + "." + std::to_string((long)getpid());
-        if (FILE *f = fopen(tmp.c_str(),"wb"))
+        const int fd = open(tmp.c_str(),O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW | O_CLOEXEC,0600);
+        FILE *f = fd >= 0 ? fdopen(fd,"wb") : nullptr;
+        if (!f && fd >= 0)
+            close(fd);
+        if (f)
         {
-            const bool ok = fwrite(entry.data(),1,entry.size(),f) == entry.size();
-            fclose(f);
-            if (!ok || rename(tmp.c_str(),path.c_str()) != 0)
+            const bool ok = fwrite(&hd,1,sizeof(hd),f) == sizeof(hd) &&
+                fwrite(entry.data(),1,entry.size(),f) == entry.size();
+            const bool closed = fclose(f) == 0;
+            if (!ok || !closed || rename(tmp.c_str(),path.c_str()) != 0)
                 unlink(tmp.c_str());
         }
     }
     std::lock_guard<std::mutex> lock(mu);
-    mem_cache[h] = entry;
+    mem_cache[std::make_pair(h,h2)] = entry;
     return true;
 }
 

@@ -783,6 +783,54 @@ __global__ void add_buffer_kernel(typename Real<T>::word *__restrict__ dst,
     }
 }
 
+/* K2d: the multi-GPU exchange step as a reduce-scatter over peer memory. The device that owns
+   elements [first, first + n) of the buffer adds the same slice of every other device's private
+   buffer to its own, reading the peers directly over NVLink (or, under one process per GPU, the
+   slices an all-to-all delivered), typed by position like K2 (element 0 of a cell is a count, the
+   rest are colour sums). All devices run this at once on different slices, so every NVLink
+   port carries 1/N of the buffer per peer instead of device 0 pulling N-1 whole buffers. */
+#define FFR_MAX_PEERS 15
+struct PeerSlices { const void *src[FFR_MAX_PEERS]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_slices_kernel(typename Real<T>::word *__restrict__ dst,
+        const PeerSlices peers, int n_src, u64 first_elem, u64 n_elems, uint32_t cellsz)
+{
+    typedef typename Real<T>::word W;
+    const u64 stride = (u64)gridDim.x*blockDim.x;
+    for (u64 i = (u64)blockIdx.x*blockDim.x + threadIdx.x; i < n_elems; i += stride)
+    {
+        W v[FFR_MAX_PEERS];
+#pragma unroll
+        for (int k = 0; k < FFR_MAX_PEERS; ++k)
+            if (k < n_src)
+                v[k] = __ldcs((const W*)peers.src[k] + i);     /* read once, keep out of the caches */
+        W d = dst[i];
+        if (cellsz == 1 || (first_elem + i) % cellsz == 0)
+        {
+#pragma unroll
+            for (int k = 0; k < FFR_MAX_PEERS; ++k)
+                if (k < n_src)
+                    d += v[k];
+        }
+        else
+        {
+            T a;
+            memcpy(&a,&d,sizeof(T));
+#pragma unroll
+            for (int k = 0; k < FFR_MAX_PEERS; ++k)
+                if (k < n_src)
+                {
+                    T b;
+                    memcpy(&b,&v[k],sizeof(T));
+                    a += b;
+                }
+            memcpy(&d,&a,sizeof(T));
+        }
+        dst[i] = d;
+    }
+}
+
 /* K3: histogramSum / histogramMax, buffer_renderer.hpp:483-509 */
 template <typename W>
 __global__ void hist_sum_max_kernel(const W *__restrict__ buf, u64 cells, uint32_t cellsz,
@@ -933,37 +981,63 @@ __global__ void __launch_bounds__(FFR_TPB) isaac_words_kernel(u64 seed, u64 n, u
             out[i] = (u64)rng.next();
 }
 
-/* M1b: attractor replay: the same RED mix at the cell indices a render of this flame produced
-   (FFR_SCATTER_TRACE), thread k replaying chain k in order, so warps collide on hot cells
-   exactly as the render's warps do -- the measured scatter roofline for THIS access pattern. */
+/* M1b: attractor replay -- the scatter of a render WITHOUT the chaos game in front of it: bare
+   REDs at exactly the addresses a render of this flame scattered to (FFR_SCATTER_TRACE records
+   them: the buffer cell, or -- bit 63 set -- the cell of the kernel's own accumulation tile after
+   the scramble / row directory). This is the measured ceiling of that render's scatter step: the
+   render can approach it but not beat it.
+   Built to SATURATE the atomic units rather than to wait on its trace: 2048 resident threads per
+   SM, each with 8 independent 128-bit trace loads in flight and then 16 REDs (which return
+   nothing, so nothing waits on them). Entry j of iteration `it` belongs to chain j, so a warp
+   replays 64 chains at the same iteration and collides on hot cells as the render's warps do. */
+#define FFR_REPLAY_TPB 256
+#define FFR_REPLAY_UNROLL 8
 template <typename T>
-__global__ void __launch_bounds__(FFR_TPB) atomic_replay_kernel(typename Real<T>::word *buffer,
-        const u64 *__restrict__ trace, u64 chain_count, u64 chain_len, uint32_t cellsz)
+__global__ void __launch_bounds__(FFR_REPLAY_TPB,8) atomic_replay_kernel(typename Real<T>::word *buffer,
+        typename Real<T>::word *tile, const ulonglong2 *__restrict__ trace, u64 n_pairs, uint32_t cellsz)
 {
     typedef typename Real<T>::word W;
-    const u64 k = (u64)blockIdx.x*blockDim.x + threadIdx.x;
-    if (k >= chain_count)
-        return;
-    for (u64 it = 0; it < chain_len; ++it)
+    const u64 stride = (u64)gridDim.x*FFR_REPLAY_TPB*FFR_REPLAY_UNROLL;
+    for (u64 base = (u64)blockIdx.x*FFR_REPLAY_TPB*FFR_REPLAY_UNROLL + threadIdx.x; base < n_pairs; base += stride)
     {
-        const u64 bi = trace[it*chain_count + k];
-        if (bi == ~0ULL)
-            continue;
-        W *cell = buffer + bi*cellsz;
-        hist_add(cell,1u);
-        for (uint32_t i = 1; i < cellsz; ++i)
-            atomicAdd((T*)(cell + i),(T)0.5);
+        ulonglong2 e[FFR_REPLAY_UNROLL];
+#pragma unroll
+        for (int j = 0; j < FFR_REPLAY_UNROLL; ++j)
+        {
+            const u64 at = base + (u64)j*FFR_REPLAY_TPB;
+            e[j] = at < n_pairs ? __ldcs(&trace[at]) : make_ulonglong2(~0ULL,~0ULL);
+        }
+#pragma unroll
+        for (int j = 0; j < FFR_REPLAY_UNROLL; ++j)
+        {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+            {
+                const u64 bi = h ? e[j].y : e[j].x;
+                if (bi == ~0ULL)
+                    continue;
+                W *cell = (bi >> 63) ? tile + (bi & ~(1ULL << 63)) : buffer + bi*cellsz;
+                hist_add(cell,1u);
+                for (uint32_t i = 1; i < cellsz; ++i)
+                    atomicAdd((T*)(cell + i),(T)0.5);
+            }
+        }
     }
 }
 
 /* M1: random-atomic microbenchmark: same RED mix as the render kernel's scatter (1 count +
-   r colour sums per cell) at uniformly random cells, no chaos game in front of it. */
+   r colour sums per cell) at uniformly random cells of the buffer, no chaos game in front of
+   it; same launch shape as the replay (2048 threads per SM, REDs issued back to back). A
+   reference point for the memory system at this buffer size, NOT a ceiling for a render: an
+   attractor concentrates its samples on few cells and can stay L2-resident in a buffer that
+   uniform addresses stream from HBM. */
 template <typename T>
-__global__ void __launch_bounds__(FFR_TPB) atomic_bench_kernel(typename Real<T>::word *buffer, u64 cells,
+__global__ void __launch_bounds__(FFR_REPLAY_TPB,8) atomic_bench_kernel(typename Real<T>::word *buffer, u64 cells,
         uint32_t cellsz, u64 per_thread, u64 seed)
 {
     typedef typename Real<T>::word W;
     u64 s = splitmix64(seed + (u64)blockIdx.x*blockDim.x + threadIdx.x);
+#pragma unroll 8
     for (u64 k = 0; k < per_thread; ++k)
     {
         /* xorshift64* */

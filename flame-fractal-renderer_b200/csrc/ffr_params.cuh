@@ -27,8 +27,9 @@ struct RenderParams
     DevStats *stats;
     unsigned int *work_counter;
     void *rsl_scratch;             /* K1b: randrsl columns, 16*FFR_TPB words per block */
-    u64 *trace;                    /* FFR_SCATTER_TRACE: cell index of sample `it` of chain k at
-                                      trace[it*chain_count + k], ~0 when not plotted */
+    u64 *trace;                    /* FFR_SCATTER_TRACE: where sample `it` of chain k was scattered to, at
+                                      trace[it*chain_count + k]: the buffer cell index, or bit 63 | the
+                                      element index in `acc` (K1e's tiles); ~0 when not plotted */
     u64 chain_first, chain_count, chain_len, last_len, base_seed, bv_limit;
     uint32_t blob_bytes, scatter_mode;
     void *acc;                     /* K1e: accumulation tile (or null): scrambled cell order, folded into

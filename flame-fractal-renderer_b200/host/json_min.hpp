@@ -593,7 +593,7 @@ public:
             int e = n - 1;
             out += e < 0 ? '-' : '+';
             if (e < 0) e = -e;
-            char eb[8];
+            char eb[16];
             snprintf(eb,sizeof(eb),"%02d",e);
             out += eb;
         }

@@ -233,7 +233,11 @@ enum ffr_scatter_mode
     FFR_SCATTER_AUTO = 0,
     FFR_SCATTER_GLOBAL = 1,     /* one RED per element straight to L2/HBM */
     FFR_SCATTER_WARP_AGG = 2,   /* __match_any_sync aggregation of colliding lanes first */
-    FFR_SCATTER_SMEM_TILE = 3,  /* shared-memory privatised hot tile + global fallback */
+    FFR_SCATTER_SMEM_TILE = 3,  /* reserved, NOT implemented: ffr_cuda_create_ex fails with a message.
+                                   A shared-memory privatised tile has no room next to the chains'
+                                   ISAAC state (scatter strategies); what the library does
+                                   instead for small/mid buffers is the L2-resident accumulation tile
+                                   of the pure-affine kernel, chosen automatically */
     FFR_SCATTER_TRACE = 5,      /* internal to ffr_cuda_atomic_roofline pattern 1 */
     FFR_SCATTER_DISCARD = 4     /* diagnostic: iterate and count but issue no REDs (measures the
                                    compute-only rate for the roofline analysis; buffer untouched) */
@@ -347,8 +351,18 @@ int ffr_cuda_jit_compile(const ffr_flame_desc *desc, char *source, size_t source
         size_t *cubin_bytes, char *err, size_t errlen);
 
 /* Sum the per-device private buffers into device 0's buffer over NVLink peer memory
-   (no-op for one device). ffr_cuda_read_buffer calls it when needed. */
+   (no-op for one device): a reduce-scatter -- every device adds its 1/N slice of all peers'
+   buffers, reading them in place, all devices at once -- then device 0 gathers the finished
+   slices. ffr_cuda_read_buffer calls it when needed. */
 int ffr_cuda_reduce(ffr_ctx *ctx);
+
+/* The same typed slice sum for hosts that run one process per GPU and exchange buffer slices
+   themselves (an all-to-all over NCCL): dst[i] += sum_k srcs[k][i] for n_elems elements, all
+   DEVICE pointers on the context's device, element i being element first_elem + i of the buffer
+   (element 0 of each cell adds as a count, the others as colour sums). n_src <= 15. Launched on
+   the context's stream, not synchronised. */
+int ffr_cuda_sum_device_slices(ffr_ctx *ctx, void *dst, const void *const *srcs, int n_src,
+        uint64_t first_elem, uint64_t n_elems);
 
 /* writeBuffer (buffer_renderer.hpp:476-480): the reduced buffer in the reference file
    layout: cells x [count u64, c0..c(r-1) f64], dimension 0 fastest, native endian. */
