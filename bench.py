@@ -7,10 +7,10 @@
 
 A step = one pass of the hot path over one batch of chains: `chains_per_step` independent
 chains of `chain_len` samples per GPU (a whole number of "waves" of resident chain groups),
-rendered into the GPU's private buffer. The workload (default) is the north-star target config:
-csci6360_project at 4096x4096, double/u64, counts only. Weak scaling: every rank renders its
-own disjoint chain range (no data-path collective); for N > 1 the timed region ends with the
-one exchange step the path has, the sum-reduce of the private buffers to rank 0 over
+rendered into the GPU's private buffer. The headline workload (default) is the north-star target
+config: csci6360_project at 4096x4096, double/u64, counts only. Weak scaling: every rank
+renders its own disjoint chain range (no data-path collective); for N > 1 the timed region ends
+with the one exchange step the path has, the sum-reduce of the private buffers to rank 0 over
 NCCL/NVLink. Prints ONE JSON line on rank 0.
 
 value     device-timed (CUDA events on the launching stream) throughput of K steps with
@@ -21,8 +21,16 @@ e2e       the same metric through the reference-facing C ABI with HOST buffers: 
           buffer back (ffr_cuda_read_buffer) -- H2D and D2H inside the timed region.
 roofline  HBM: algorithmic bytes (one RMW of one cell per PLOTTED sample = 2*(1+r)*8 B) per
           launch / average launch duration, against MEASURED_PEAKS.json hbm_gbs.
+atomic_roofline  the north star's denominator: bare REDs at the addresses this render scatters
+          to (attractor replay, a saturating microbenchmark: the render's scatter ceiling), and
+          at uniformly random cells of the same buffer (a reference point, not a ceiling).
 cpu_baseline  the unmodified reference (oracle/_ref, BufferRenderer::render) on all host
           cores for a bounded sample of the same workload.
+configs   (N = 1, default run) the five BASELINE.json configurations measured the same way, each
+          timed >= ~1.2 s with its own clock record; cfg5 (8 GPUs) appears as its per-GPU shard.
+strong_scaling  BASELINE config 5 as stated: csci6360_project at 8192^2, a FIXED 1e11 samples
+          split over the N ranks, with the buffer reduce and the read-back to the host inside the
+          timed region (the weak-scaling headline cannot bend; this curve can).
 """
 
 import argparse
@@ -47,19 +55,40 @@ WORKLOADS = {
     "barnsley_2048": ("barnsley_fern", [2048, 2048], 8192),
     "tkoz_test3_4096": ("tkoz_test3", [4096, 4096], 8192),
     "sierpinski3d_512": ("sierpinski_triangle_3d", [512, 512, 512], 8192),
+    "barnsley_8192": ("barnsley_fern", [8192, 8192], 8192),
 }
 DEFAULT_WORKLOAD = "csci6360_4096"
+# BASELINE.json "configs", in order
+BASELINE_CONFIGS = [("cfg1", "sierpinski_1024"), ("cfg2", "barnsley_2048"), ("cfg3", "tkoz_test3_4096"),
+                    ("cfg4", "sierpinski3d_512"), ("cfg5 (per-GPU shard of the 8-GPU job)", "csci6360_8192")]
+STRONG_WORKLOAD, STRONG_SAMPLES = "csci6360_8192", 100_000_000_000
 METRIC = "chaos-game samples/sec into buffer"
 UNIT = "samples/s"
 
+# What bounds each workload's render kernel (with the ncu evidence)
+BOUND_NOTE = {
+    "csci6360_4096": "K1d is instruction-issue / fp64-pipe bound (13 transcendental variations over 5 "
+                     "xforms); the scatter is hidden behind the arithmetic and HBM is < 5 % busy",
+    "csci6360_8192": "as csci6360_4096; the 512 MiB buffer no longer fits L2 but the scatter stays hidden",
+    "tkoz_test3_4096": "K1d, instruction-issue / fp64-pipe bound; 4 REDs per plotted sample (count + 3 "
+                       "colour sums, one 32-byte sector)",
+    "sierpinski_1024": "K1e, bound by the L2 atomic units (one RED sector per sample into the "
+                       "cell-scrambled L2-resident tile); DRAM idle",
+    "barnsley_2048": "K1e, bound by the L2 atomic units (cell-scrambled L2-resident tile); DRAM idle",
+    "sierpinski3d_512": "K1e + compact tile: L2 atomic units + one row-directory lookup per sample; "
+                        "the hot rows are L2-resident inside the 1 GiB buffer",
+    "barnsley_8192": "K1e + compact tile, dense attractor: part of the rows overflow the tile and "
+                     "scatter into the 512 MiB buffer directly",
+}
 
 # dram__bytes_read.sum + dram__bytes_write.sum per PLOTTED sample of the render kernel, from the
-# committed `ncu --set full` captures (profiles/README.md); traffic per launch = this x plotted
+# committed `ncu --set full` captures (profiles/README.md); traffic per launch = this x plotted.
+# A workload without a capture reports null.
 NCU_DRAM_BYTES_PER_PLOTTED = {
-    "csci6360_4096": (0.4210e9 + 3.8049e9) / 500.0e6,   # profiles/r1_k1d_csci4096_sincos (500.0e6 plotted = RED sectors)
-    "tkoz_test3_4096": (1.8337e9 + 6.6085e9) / 327.7e6,  # profiles/r1_k1d_tkoz3_4096
-    "sierpinski3d_512": (8.99e6 + 0.006e6) / 1862.3e6,  # profiles/r1_k1e_sierp3d_512_compact_tile
-    "barnsley_2048": (25.83e6 + 0.008e6) / 1862.3e6,    # profiles/r1_k1e_barnsley2048
+    "csci6360_4096": ((0.4210e9 + 3.8049e9) / 500.0e6, "profiles/r1_k1d_csci4096_sincos.summary.txt"),
+    "tkoz_test3_4096": ((1.8337e9 + 6.6085e9) / 327.7e6, "profiles/r1_k1d_tkoz3_4096.summary.txt"),
+    "sierpinski3d_512": ((8.99e6 + 0.006e6) / 1862.3e6, "profiles/r1_k1e_sierp3d_512_compact_tile.summary.txt"),
+    "barnsley_2048": ((25.83e6 + 0.008e6) / 1862.3e6, "profiles/r1_k1e_barnsley2048.summary.txt"),
 }
 
 
@@ -72,7 +101,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (recipe's clocks line)."""
+    """nvidia-smi clocks + throttle reasons DURING the timed regions (recipe's clocks line).
+    One nvidia-smi process for the whole run; mark()/window() cut out a region."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -82,12 +112,13 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.t0 = 0.0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -99,23 +130,15 @@ class ClockSampler:
             self.lines.append((time.monotonic(), line.strip()))
 
     def mark(self):
-        """Start of the timed region: only samples taken from here to stop() are reported
-        (the sampler itself is started before the warm-up so that nvidia-smi's start-up time
-        does not eat the region)."""
+        """Start of a timed region: only samples taken from here to window() are reported."""
         self.t0 = time.monotonic()
 
-    def stop(self):
+    def window(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         t1 = time.monotonic()
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
-        t0 = getattr(self, "t0", 0.0)
-        window = [(ts, ln) for ts, ln in list(self.lines) if t0 <= ts <= t1]
+        window = [(ts, ln) for ts, ln in list(self.lines) if self.t0 <= ts <= t1]
         if not window:      # region shorter than one sampling period: the nearest samples
             window = list(self.lines)[-2:]
         for ts, ln in window:
@@ -138,38 +161,56 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
 
-def run_reference(args, wl_name):
-    """--impl reference: the reference's own CPU implementation of the path
-    (BufferRenderer::render through oracle/_ref, unmodified sources) on all host threads."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+
+def cpu_reference(wl_name, sample, cores=None):
+    """The reference's own CPU implementation of the path (BufferRenderer::render through
+    oracle/_ref, unmodified sources; the oracle port if _ref is absent) on `cores` host threads."""
     import pyoracle as po
     ex = importlib.import_module("flame-fractal-renderer_b200.examples")
     ename, size, _ = WORKLOADS[wl_name]
     text = ex.example_json(ename, size=size)
-    cores = os.cpu_count() or 1
-    have_ref = po.have_ref()
-    sample = args.ref_samples
+    cores = cores or os.cpu_count() or 1
     batch = max(4096, min(1 << 20, (sample + 255) >> 8))  # ffr_buf.cpp:94-101
-
-    def one_step():
-        if have_ref:
-            secs, st, _ = po.ref_render_mt(text, sample, cores, batch)
-            return secs
+    if po.have_ref():
+        secs, _, _ = po.ref_render_mt(text, sample, cores, batch)
+        kind = "reference"
+    else:
         ffr = importlib.import_module("flame-fractal-renderer_b200")
         fl = ffr.Flame(text)
         t0 = time.perf_counter()
         po.oracle_render_samples(fl, sample, batch, nthreads=cores)
-        return time.perf_counter() - t0
+        secs = time.perf_counter() - t0
+        kind = "port"
+    return {"value": sample / secs, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d samples of %s, BufferRenderer::render with %d threads, batch %d, %.1f s"
+                      % (sample, wl_name, cores, batch, secs)}, secs, batch
 
+
+def run_reference(args, wl_name):
+    """--impl reference: times the reference's CPU implementation on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ename, size, _ = WORKLOADS[wl_name]
+    cores = os.cpu_count() or 1
+    sample = args.ref_samples
     for _ in range(args.warmup):
-        one_step()
-    t = [one_step() for _ in range(args.steps)]
-    total = sum(t)
+        cpu_reference(wl_name, sample, cores)
+    total, kind, batch = 0.0, "reference", 0
+    for _ in range(args.steps):
+        c, secs, batch = cpu_reference(wl_name, sample, cores)
+        kind = c["kind"]
+        total += secs
     value = sample * args.steps / total
-    kind = "reference" if have_ref else "port"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -186,6 +227,287 @@ def run_reference(args, wl_name):
     print(json.dumps(line), flush=True)
 
 
+class Bench:
+    """State shared by the measurements of one process (rank)."""
+
+    def __init__(self, args):
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        self.np, self.torch, self.dist = np, torch, dist
+        self.args = args
+        self.ffr = importlib.import_module("flame-fractal-renderer_b200")
+        self.ex = importlib.import_module("flame-fractal-renderer_b200.examples")
+        self.sharding = importlib.import_module("flame-fractal-renderer_b200.sharding")
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; there is no CPU path to measure")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", rank=self.rank, world_size=self.world, device_id=self.dev)
+        # a dedicated (non-default) stream: handle 0 would mean "library-owned stream" to the ABI
+        self.stream = torch.cuda.Stream(self.dev)
+        torch.cuda.set_stream(self.stream)
+        self.sampler = ClockSampler(self.local_rank)
+        if self.rank == 0:
+            self.sampler.start()
+        self.hbm_peak, self.peak_src = measured_peaks()
+        self.jit = self.ffr.JIT_ON if args.jit < 0 else args.jit
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------------------------------
+    def measure(self, wl_name, steps, warmup, min_seconds=0.0, ref_samples=0):
+        """One workload: device-timed value, roofline, atomic rooflines, e2e, clocks."""
+        torch, np, ffr, sharding = self.torch, self.np, self.ffr, self.sharding
+        rank, world, dev, stream = self.rank, self.world, self.dev, self.stream
+        ename, size, L = WORKLOADS[wl_name]
+        flame = ffr.Flame(self.ex.example_json(ename, size=size))
+        _, _, cells, cell = flame.layout()
+        r_dims = flame.color_dims
+        n_elems = cells * cell
+
+        # torch owns the device memory and the stream; the library renders into it
+        buf = torch.zeros(n_elems, dtype=torch.int64, device=dev)
+        # the flame-specialised kernel is compiled (NVRTC, cached) when the context is created,
+        # i.e. outside every timed region, like the ahead-of-time build of the interpreter kernels
+        t_create = time.perf_counter()
+        rend = ffr.BufferRenderer(flame, devices=[self.local_rank], external_buffer=buf.data_ptr(),
+                                  stream=stream.cuda_stream, scatter_mode=self.args.scatter, jit=self.jit)
+        t_create = time.perf_counter() - t_create
+        jit_info = rend.jit_info
+        # one wave = every resident block (SMs x blocks/SM) takes one chain group
+        chains_per_step = rend.resident_chains * self.args.waves
+        samples_per_step = chains_per_step * L
+
+        def launch_step(step_index):
+            # disjoint chain ranges: per step and per rank (weak scaling)
+            first = sharding.step_chain_range(step_index, rank, world, chains_per_step)
+            rend.render_chains_async(first, chains_per_step, L, base_seed=1)
+
+        # ---- warm-up (>= 3 steps) ----
+        warmup = max(warmup, 3)
+        launch_step(2_000_000)
+        self.barrier()
+        t_w = time.perf_counter()
+        for w in range(warmup):
+            launch_step(1_000_000 + w)
+        self.barrier()
+        step_s = (time.perf_counter() - t_w) / warmup
+        if min_seconds > 0:
+            steps = max(steps, int(min_seconds / max(step_s, 1e-4)) + 1)
+        buf.zero_()
+        st0 = rend.fetch_stats()
+        launches0 = rend.launches
+
+        # ---- timed region: K steps (+ the final buffer reduce for N > 1) ----
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev_k = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        self.barrier()
+        self.sampler.mark()
+        ev0.record(stream)
+        ev_k[0].record(stream)
+        for k in range(steps):
+            launch_step(k)
+            ev_k[k + 1].record(stream)
+        sharding.reduce_buffer(buf, cells, cell, dst=0, renderer=rend)
+        ev1.record(stream)
+        self.barrier()
+        ms_total = self.max_over_ranks(ev0.elapsed_time(ev1))
+        kernel_ms = [ev_k[k].elapsed_time(ev_k[k + 1]) for k in range(steps)]
+        clocks = self.sampler.window() if rank == 0 else None
+        st1 = rend.fetch_stats()
+        launches = rend.launches - launches0
+        plotted = st1["s_plot"] - st0["s_plot"]
+        iterated = st1["s_iter"] - st0["s_iter"]
+        assert iterated == samples_per_step * steps, (iterated, samples_per_step * steps)
+        total_samples = samples_per_step * steps * world
+        value = total_samples / (ms_total * 1e-3)
+
+        # roofline of the dominant kernel, per launch on this rank
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        alg_bytes = plotted / steps * 2 * (1 + r_dims) * 8
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        plotted_per_s = plotted / steps / (k_ms * 1e-3)
+
+        # measured atomic-scatter rooflines on the same buffer (SURVEY 8d), three runs each
+        atomic = None
+        if rank == 0:
+            rend.atomic_roofline(1 << 26)
+            rend.atomic_roofline(1 << 26, pattern=1)
+            uni, rep = [], []
+            for _ in range(3):
+                ms, n_at = rend.atomic_roofline(1 << 30)
+                uni.append(n_at / (ms * 1e-3))
+                ms, n_rp = rend.atomic_roofline(1 << 28, pattern=1)
+                rep.append(n_rp / (ms * 1e-3))
+            uni.sort()
+            rep.sort()
+            atomic = {"ceiling": "attractor_replay",
+                      "attractor_replay_cells_per_s": rep[1], "attractor_replay_runs": rep,
+                      "uniform_random_cells_per_s": uni[1], "uniform_random_runs": uni,
+                      "plotted_samples_per_s": plotted_per_s,
+                      "frac": plotted_per_s / rep[1],
+                      "frac_of_uniform_random": plotted_per_s / uni[1],
+                      "note": "replay = bare REDs at the addresses this render scatters to (incl. K1e's "
+                              "tile scramble / row directory), 2048 threads/SM, 16 REDs in flight per "
+                              "thread: the scatter ceiling of this render. uniform random cells of the "
+                              "same buffer are a reference point only (an attractor can be L2-resident "
+                              "where uniform addresses stream from HBM)"}
+        buf.zero_()
+        self.barrier()
+
+        # ---- e2e through the C ABI with host buffers ----
+        rend.close()
+        nbytes = n_elems * 8
+        host_in = torch.zeros(n_elems, dtype=torch.int64).pin_memory()
+        host_out = torch.zeros(n_elems, dtype=torch.int64).pin_memory()
+        in_np = host_in.numpy().view(np.uint64)
+        out_np = host_out.numpy().view(np.uint64)
+        ebuf = None
+        if world > 1:
+            # multi-rank e2e: render into torch memory so NCCL can reduce it, host copies on rank 0
+            ebuf = torch.zeros(n_elems, dtype=torch.int64, device=dev)
+            e2e_rend = ffr.BufferRenderer(flame, devices=[self.local_rank], external_buffer=ebuf.data_ptr(),
+                                          stream=stream.cuda_stream, jit=self.jit)
+
+            def e2e_step(k):
+                ebuf.zero_()
+                if rank == 0:
+                    e2e_rend.add_buffer(in_np)
+                first = sharding.step_chain_range(k + 500_000, rank, world, chains_per_step)
+                e2e_rend.render_chains(first, chains_per_step, L, base_seed=1)
+                sharding.reduce_buffer(ebuf, cells, cell, dst=0, renderer=e2e_rend)
+                if rank == 0:
+                    e2e_rend.read_buffer(out_np)
+        else:
+            e2e_rend = ffr.BufferRenderer(flame, devices=[self.local_rank], jit=self.jit)
+
+            def e2e_step(k):
+                e2e_rend.clear()
+                e2e_rend.add_buffer(in_np)
+                first = (k + 500_000) * chains_per_step
+                e2e_rend.render_chains(first, chains_per_step, L, base_seed=1)
+                e2e_rend.read_buffer(out_np)
+
+        e2e_steps = max(3, min(steps, 20))
+        e2e_step(-1)
+        self.barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            e2e_step(k)
+        self.barrier()
+        e2e_s = self.max_over_ranks(time.perf_counter() - t0)
+        e2e_value = samples_per_step * e2e_steps * world / e2e_s
+        e2e_rend.close()
+        del buf, ebuf, host_in, host_out, in_np, out_np
+        torch.cuda.empty_cache()
+
+        cpu = None
+        if rank == 0 and world == 1 and ref_samples > 0:
+            cpu, _, _ = cpu_reference(wl_name, ref_samples)
+        if rank != 0:
+            return None
+        traffic = None
+        traffic_src = None
+        if wl_name in NCU_DRAM_BYTES_PER_PLOTTED:
+            per, traffic_src = NCU_DRAM_BYTES_PER_PLOTTED[wl_name]
+            traffic = per * plotted / steps
+        kernel = ("flame-specialised, compiled at context creation (NVRTC %.1f s%s, context %.1f s): "
+                  "%d threads x %d blocks/SM, %d chain slots/block, %d registers; %s"
+                  % (jit_info["compile_seconds"], ", cached" if jit_info["from_cache"] else "", t_create,
+                     jit_info["threads_per_block"], jit_info["blocks_per_sm"], jit_info["slots_per_block"],
+                     jit_info["registers"], jit_info["message"].strip())
+                  if jit_info["active"] else "ahead-of-time interpreter kernel")
+        return {
+            "value": value, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+            "timed_seconds": ms_total * 1e-3,
+            "config": {"workload": wl_name, "flame": ename, "size": size, "color_dims": r_dims,
+                       "chain_len": L, "chains_per_step_per_gpu": chains_per_step,
+                       "samples_per_step_per_gpu": samples_per_step, "base_seed": 1,
+                       "kernel": kernel,
+                       "parallelism": "chain-range sharding x%d, private buffers, final NCCL sum-reduce" % world,
+                       "l2": "no flush: the only memory operand is the %.0f MiB accumulation buffer (L2 is "
+                             "126 MB), which a render keeps resident across steps; samples are generated "
+                             "on device" % (n_elems * 8 / 2**20)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+                    "d2h_bytes_per_step": nbytes, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": self.hbm_peak, "unit": "GB/s",
+                         "frac": achieved / self.hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": self.peak_src, "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "plotted_fraction": plotted / iterated,
+                         "limiter": BOUND_NOTE.get(wl_name)},
+            "atomic_roofline": atomic,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+
+    # ------------------------------------------------------------------------------------------
+    def strong(self):
+        """BASELINE config 5 as stated: a FIXED 1e11 samples of csci6360_project at 8192^2 split over
+        the ranks (contiguous chain ranges), private buffers, ONE sum-reduce to rank 0 and the
+        read-back of the 512 MiB result to the host -- all inside the timed region."""
+        torch, ffr, sharding = self.torch, self.ffr, self.sharding
+        ename, size, L = WORKLOADS[STRONG_WORKLOAD]
+        flame = ffr.Flame(self.ex.example_json(ename, size=size))
+        _, _, cells, cell = flame.layout()
+        n_elems = cells * cell
+        total = self.args.strong_samples
+        chains = (total + L - 1) // L
+        first, count = sharding.split_chains(chains, self.world)[self.rank]
+        buf = torch.zeros(n_elems, dtype=torch.int64, device=self.dev)
+        rend = ffr.BufferRenderer(flame, devices=[self.local_rank], external_buffer=buf.data_ptr(),
+                                  stream=self.stream.cuda_stream, jit=self.jit)
+        host = torch.zeros(n_elems, dtype=torch.int64).pin_memory()
+        rend.render_chains_async(10_000_000_000, rend.resident_chains, L, base_seed=1)   # warm
+        self.barrier()
+        buf.zero_()
+        self.barrier()
+        self.sampler.mark()
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record(self.stream)
+        rend.render_chains_async(first, count, L, base_seed=1)
+        sharding.reduce_buffer(buf, cells, cell, dst=0, renderer=rend)
+        if self.rank == 0:
+            host.copy_(buf, non_blocking=True)
+        ev1.record(self.stream)
+        self.barrier()
+        wall = self.max_over_ranks(time.perf_counter() - t0)
+        ms = self.max_over_ranks(ev0.elapsed_time(ev1))
+        clocks = self.sampler.window() if self.rank == 0 else None
+        plotted = int(host.sum().item()) if self.rank == 0 else 0
+        rend.close()
+        del buf, host
+        torch.cuda.empty_cache()
+        if self.rank != 0:
+            return None
+        return {"workload": STRONG_WORKLOAD, "scaling": "strong", "total_samples": chains * L,
+                "n_gpus": self.world, "seconds": ms * 1e-3, "wall_seconds": wall,
+                "value": chains * L / (ms * 1e-3), "unit": UNIT, "plotted": plotted,
+                "includes": "render of this rank's chain range + buffer sum-reduce to rank 0 + D2H of "
+                            "the %.0f MiB result" % (n_elems * 8 / 2**20),
+                "clocks": clocks}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,6 +520,10 @@ def main():
     ap.add_argument("--ref-samples", type=int, default=100_000_000,
                     help="bounded CPU sample per step for the reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the per-config measurements of the five BASELINE configs (N = 1)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the fixed-size cfg5 run")
+    ap.add_argument("--strong-samples", type=int, default=STRONG_SAMPLES)
     ap.add_argument("--scatter", type=int, default=0)
     ap.add_argument("--jit", type=int, default=-1,
                     help="run-time compiled flame-specialised kernel: -1 = on for flames with "
@@ -208,229 +534,39 @@ def main():
         run_reference(args, wl_name)
         return
 
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    ffr = importlib.import_module("flame-fractal-renderer_b200")
-    ex = importlib.import_module("flame-fractal-renderer_b200.examples")
-    sharding = importlib.import_module("flame-fractal-renderer_b200.sharding")
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; there is no CPU path to measure")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-
-    ename, size, L = WORKLOADS[wl_name]
-    flame = ffr.Flame(ex.example_json(ename, size=size))
-    _, _, cells, cell = flame.layout()
-    r_dims = flame.color_dims
-    n_elems = cells * cell
-
-    # torch owns the device memory and the stream; the library renders into it
-    buf = torch.zeros(n_elems, dtype=torch.int64, device=dev)
-    # a dedicated (non-default) stream: handle 0 would mean "library-owned stream" to the ABI
-    stream = torch.cuda.Stream(dev)
-    torch.cuda.set_stream(stream)
-    # the flame-specialised kernel is compiled (NVRTC, cached) when the context is created, i.e.
-    # outside every timed region, like the ahead-of-time build of the interpreter kernels
-    jit = args.jit
-    if jit < 0:
-        jit = ffr.JIT_ON   # flame-specialised kernels: K1d (variations), K1e (pure-affine flames)
-    t_create = time.perf_counter()
-    rend = ffr.BufferRenderer(flame, devices=[local_rank], external_buffer=buf.data_ptr(),
-                              stream=stream.cuda_stream, scatter_mode=args.scatter, jit=jit)
-    t_create = time.perf_counter() - t_create
-    jit_info = rend.jit_info
-    # one wave = every resident block (SMs x blocks/SM) takes one chain group of 256 chains
-    chains_per_step = rend.resident_chains * args.waves
-    samples_per_step = chains_per_step * L
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def launch_step(step_index):
-        # disjoint chain ranges: per step and per rank (weak scaling)
-        first = sharding.step_chain_range(step_index, rank, world, chains_per_step)
-        rend.render_chains_async(first, chains_per_step, L, base_seed=1)
-
-    def reduce_to_rank0():
-        sharding.reduce_buffer(buf, cells, cell, dst=0, renderer=rend)
-
-    # ---- warm-up (>= 3 steps); the clock sampler starts here, reports the timed region only ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    for w in range(max(args.warmup, 0)):
-        launch_step(1_000_000 + w)
-    barrier()
-    buf.zero_()
-    st0 = rend.fetch_stats()
-    launches0 = rend.launches
-
-    # ---- timed region: K steps (+ the final buffer reduce for N > 1) ----
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    ev_k = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    sampler.mark()
-    ev0.record(stream)
-    ev_k[0].record(stream)
-    for k in range(args.steps):
-        launch_step(k)
-        ev_k[k + 1].record(stream)
-    reduce_to_rank0()
-    ev1.record(stream)
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    kernel_ms = [ev_k[k].elapsed_time(ev_k[k + 1]) for k in range(args.steps)]
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    st1 = rend.fetch_stats()
-    launches = rend.launches - launches0
-    plotted = st1["s_plot"] - st0["s_plot"]
-    iterated = st1["s_iter"] - st0["s_iter"]
-    assert iterated == samples_per_step * args.steps, (iterated, samples_per_step * args.steps)
-    total_samples = samples_per_step * args.steps * world
-    value = total_samples / (ms_total * 1e-3)
-
-    # roofline of the dominant (only) kernel, per launch on this rank
-    hbm_peak, peak_src = measured_peaks()
-    k_ms = sum(kernel_ms) / len(kernel_ms)
-    alg_bytes = plotted / args.steps * 2 * (1 + r_dims) * 8
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-
-    # measured atomic-scatter rooflines on the same buffer: uniformly random cells,
-    # and a replay of this flame's own attractor trace (same warps, same hot-cell collisions)
-    rend.atomic_roofline(1 << 28)  # warm
-    atomic_ms, n_at = rend.atomic_roofline(1 << 30)
-    atomics_per_s = n_at / (atomic_ms * 1e-3)
-    replay_ms, n_rp = rend.atomic_roofline(1 << 28, pattern=1)
-    replay_per_s = n_rp / (replay_ms * 1e-3)
-    buf.zero_()
-
-    # ---- e2e through the C ABI with host buffers ----
-    rend.close()
-    e2e_rend = ffr.BufferRenderer(flame, devices=[local_rank], jit=jit)
-    nbytes = n_elems * 8
-    host_in = torch.zeros(n_elems, dtype=torch.int64).pin_memory()
-    host_out = torch.zeros(n_elems, dtype=torch.int64).pin_memory()
-    in_np = host_in.numpy().view(np.uint64)
-    out_np = host_out.numpy().view(np.uint64)
-
-    if world > 1:
-        # multi-rank e2e: render into torch memory so NCCL can reduce it, host copies on rank 0
-        e2e_rend.close()
-        ebuf = torch.zeros(n_elems, dtype=torch.int64, device=dev)
-        e2e_rend = ffr.BufferRenderer(flame, devices=[local_rank], external_buffer=ebuf.data_ptr(),
-                                      stream=stream.cuda_stream, jit=jit)
-
-        def e2e_step(k):
-            ebuf.zero_()
-            if rank == 0:
-                e2e_rend.add_buffer(in_np)
-            first = sharding.step_chain_range(k + 500_000, rank, world, chains_per_step)
-            e2e_rend.render_chains(first, chains_per_step, L, base_seed=1)
-            sharding.reduce_buffer(ebuf, cells, cell, dst=0, renderer=e2e_rend)
-            if rank == 0:
-                e2e_rend.read_buffer(out_np)
-    else:
-        def e2e_step(k):
-            e2e_rend.clear()
-            e2e_rend.add_buffer(in_np)
-            first = (k + 500_000) * chains_per_step
-            e2e_rend.render_chains(first, chains_per_step, L, base_seed=1)
-            e2e_rend.read_buffer(out_np)
-
-    e2e_step(-1)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        e2e_step(k)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = total_samples / e2e_s
-    e2e_rend.close()
-
-    # ---- CPU baseline: the unmodified reference on the host cores (rank 0, N == 1 only) ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import pyoracle as po
-        cores = os.cpu_count() or 1
-        text = ex.example_json(ename, size=size)
-        sample = args.ref_samples
-        batch = max(4096, min(1 << 20, (sample + 255) >> 8))
-        if po.have_ref():
-            secs, _, _ = po.ref_render_mt(text, sample, cores, batch)
-            kind = "reference"
-        else:
-            t0 = time.perf_counter()
-            po.oracle_render_samples(flame, sample, batch, nthreads=cores)
-            secs = time.perf_counter() - t0
-            kind = "port"
-        cpu = {"value": sample / secs, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": "%d samples of %s, BufferRenderer::render with %d threads, batch %d, %.1f s"
-                         % (sample, wl_name, cores, batch, secs)}
-
-    if rank == 0:
+    b = Bench(args)
+    head = b.measure(wl_name, args.steps, args.warmup,
+                     ref_samples=0 if (args.no_cpu_baseline or b.world > 1) else args.ref_samples)
+    configs = None
+    if b.world == 1 and not args.no_configs and wl_name == DEFAULT_WORKLOAD:
+        configs = []
+        for label, name in BASELINE_CONFIGS:
+            m = b.measure(name, 3, 3, min_seconds=1.2,
+                          ref_samples=0 if args.no_cpu_baseline else 20_000_000)
+            m["baseline_config"] = label
+            m["unit"] = UNIT
+            configs.append(m)
+    strong = None
+    if not args.no_strong and wl_name == DEFAULT_WORKLOAD:
+        strong = b.strong()
+    b.sampler.stop()
+    if b.rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": b.world,
+            "steps": head["steps"], "warmup": head["warmup"], "ms_per_step": head["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_name, "flame": ename, "size": size, "color_dims": r_dims,
-                       "chain_len": L, "chains_per_step_per_gpu": chains_per_step,
-                       "samples_per_step_per_gpu": samples_per_step, "base_seed": 1,
-                       "kernel": ("flame-specialised, compiled at context creation (NVRTC %.1f s%s, "
-                                  "context %.1f s): %d threads x %d blocks/SM, %d chain slots/block, "
-                                  "%d registers; %s" % (jit_info["compile_seconds"],
-                                                    ", cached" if jit_info["from_cache"] else "",
-                                                    t_create, jit_info["threads_per_block"],
-                                                    jit_info["blocks_per_sm"], jit_info["slots_per_block"],
-                                                    jit_info["registers"], jit_info["message"].strip())
-                                  if jit_info["active"] else "ahead-of-time interpreter kernel"),
-                       "parallelism": "chain-range sharding x%d, private buffers, "
-                                      "final NCCL sum-reduce" % world,
-                       "l2": "no flush: the only memory operand is the %.0f MiB accumulation "
-                             "buffer (L2 is 126 MB), which a render keeps resident across steps; "
-                             "samples are generated on device" % (n_elems * 8 / 2**20)},
-            "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak,
-                         "traffic": (NCU_DRAM_BYTES_PER_PLOTTED[wl_name] * plotted / args.steps
-                                     if wl_name in NCU_DRAM_BYTES_PER_PLOTTED else None),
-                         "peak_source": peak_src, "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "plotted_fraction": plotted / iterated,
-                         "note": "fp64-issue bound on this flame, not HBM bound: see DESIGN.md"},
-            "atomic_roofline": {"uniform_random_cells_per_s": atomics_per_s,
-                                "attractor_replay_cells_per_s": replay_per_s,
-                                "plotted_samples_per_s": plotted / args.steps / (k_ms * 1e-3),
-                                "frac": (plotted / args.steps / (k_ms * 1e-3)) / atomics_per_s,
-                                "frac_of_replay": (plotted / args.steps / (k_ms * 1e-3)) / replay_per_s},
-            "cpu_baseline": cpu,
-            "clocks": clocks,
+            "config": head["config"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "roofline": head["roofline"], "atomic_roofline": head["atomic_roofline"],
+            "cpu_baseline": head["cpu_baseline"], "clocks": head["clocks"],
         }
+        if configs is not None:
+            line["configs"] = configs
+        if strong is not None:
+            line["strong_scaling"] = strong
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if b.world > 1:
+        b.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -657,7 +657,8 @@ bool jit_prepare(ffr_ctx *ctx, bool cache_only = false)
                 return false;
             }
             ctx->jit_compile_s += secs;
-            ctx->jit_note += std::string("K1e pure-affine kernel, ") + (cfg.acc_mul ? "scrambled accumulation tile, " : "") +
+            ctx->jit_note += std::string("K1e pure-affine kernel, ") +
+                (cfg.acc_mul ? (cfg.acc_gran ? "sector-scrambled accumulation tile, " : "cell-scrambled accumulation tile, ") : "") +
                 (cfg.dir_cap ? "compact tile of " + std::to_string(cfg.dir_cap) + " rows, " : std::string()) +
                 std::to_string(cfg.npair) + " table rows, tpb " +
                 std::to_string(cfg.tpb) + ": " + std::to_string(spills) + " spill bytes; ";
@@ -716,7 +717,8 @@ bool jit_prepare(ffr_ctx *ctx, bool cache_only = false)
             return false;
         }
         ctx->jit_compile_s += secs;
-        ctx->jit_note += "tpb " + std::to_string(cfg.tpb) + ": " + std::to_string(spills) + " spill bytes; ";
+        ctx->jit_note += std::string(cfg.async ? "K1d queue-scheduled kernel, " : "K1c lock-step kernel, ") +
+            "tpb " + std::to_string(cfg.tpb) + ": " + std::to_string(spills) + " spill bytes; ";
         /* 320 threads x 2 blocks cap the kernel at 96 registers; a flame whose xforms spill there
            runs faster with 256 threads (128 registers) than with spills through a thrashed L1 */
         if (attempt == 0 && spills > 32 && cfg.tpb > 256 && !getenv("FFR_JIT_TPB"))

@@ -128,3 +128,21 @@ def test_auto_mode_is_lazy(ffr, examples, monkeypatch):
     r.render(100000, 1000)
     assert not r.jit_info["active"]
     r.close()
+
+
+def test_few_very_long_chains_do_not_trip_the_watchdog(ffr, po, examples):
+    """with far fewer live chains than threads, almost every warp of K1d finds nothing
+    to pop for the whole launch (seconds). That is waiting, not a stall: the watchdog only counts
+    polls during which NO warp of the block popped anything. 6 chains x 1.5e6 samples of an
+    IEEE-only flame (spherical: class ii), so the result is also bit-exact against the oracle."""
+    fl = ffr.Flame(examples.example_json("flam3_test_1", size=[96, 96]))
+    r = ffr.BufferRenderer(fl, jit=ffr.JIT_ON)
+    assert "K1d queue-scheduled kernel" in r.jit_info["message"]
+    assert r.render_chains(0, 6, 1_500_000, base_seed=77, bv_limit=1 << 40)
+    got, st = r.read_buffer(), r.stats
+    r.close()
+    want, ost, _ = po.oracle_render(fl, 6, 1_500_000, base_seed=77, bv_limit=1 << 40, nthreads=6)
+    assert st["s_iter"] == 9_000_000
+    for k in ("s_iter", "s_plot", "xf_dist", "n_bad", "pt_min", "pt_max"):
+        assert st[k] == ost[k], k
+    assert np.array_equal(got, want)

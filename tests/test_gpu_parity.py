@@ -191,9 +191,13 @@ def hist_l1(a, b):
 @pytest.mark.parametrize("name,size", [("csci6360_project", [192, 108]), ("tkoz_test3", [160, 90]),
                                        ("tkoz_test1", [128, 128]), ("rectangle_maze", [128, 128]),
                                        ("sierpinski_with_variations", [128, 128]),
-                                       ("tkoz_test5", [128, 128])])
-def test_statistical_parity(ffr, po, examples, name, size):
-    """Class (iii) flames: trajectories diverge chaotically after a few ULP of libm/CUDA
+                                       ("tkoz_test5", [128, 128]),
+                                       ("tkoz_test2", [500, 200]), ("tkoz_test4", [768, 512])])
+@pytest.mark.parametrize("kernel", ["aot", "jit"])
+def test_statistical_parity(ffr, po, examples, name, size, kernel):
+    """Every variation-heavy example flame (8 of the 15; the other 7 are bit-exact, see
+    test_exact_examples), through the ahead-of-time kernels AND the run-time compiled K1d.
+    Class (iii) flames: trajectories diverge chaotically after a few ULP of libm/CUDA
     difference, so the check is statistical at equal sample count (4.2e6 samples in 8192
     chains). Chains are correlated heavy-tailed trajectories, not multinomial draws, so the
     tolerance is MEASURED: the sampling-noise floor is the largest L1 distance of the
@@ -209,7 +213,8 @@ def test_statistical_parity(ffr, po, examples, name, size):
     _, _, cells, cs = fl.layout()
     gruns = []
     for seed in (1, 90001):
-        r = ffr.BufferRenderer(fl)
+        r = ffr.BufferRenderer(fl, jit=ffr.JIT_OFF if kernel == "aot" else ffr.JIT_ON)
+        assert r.jit_info["active"] == (kernel == "jit")
         assert r.render_chains(0, chains, L, base_seed=seed)
         gc, gcol = ffr.split_counts_colors(r.read_buffer(), cells, cs - 1)
         gst = r.stats
