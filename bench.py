@@ -350,25 +350,32 @@ class Bench:
         if rank == 0:
             rend.atomic_roofline(1 << 26)
             rend.atomic_roofline(1 << 26, pattern=1)
-            uni, rep = [], []
+            rend.atomic_roofline(1 << 26, pattern=2)
+            uni, rep, win = [], [], []
             for _ in range(3):
                 ms, n_at = rend.atomic_roofline(1 << 30)
                 uni.append(n_at / (ms * 1e-3))
                 ms, n_rp = rend.atomic_roofline(1 << 28, pattern=1)
                 rep.append(n_rp / (ms * 1e-3))
+                ms, n_w = rend.atomic_roofline(1 << 29, pattern=2)
+                win.append(n_w / (ms * 1e-3))
             uni.sort()
             rep.sort()
-            atomic = {"ceiling": "attractor_replay",
-                      "attractor_replay_cells_per_s": rep[1], "attractor_replay_runs": rep,
+            win.sort()
+            ceiling = max(rep[1], win[1])
+            atomic = {"ceiling": "attractor replay (better of streamed / windowed)",
+                      "attractor_replay_cells_per_s": ceiling,
+                      "replay_streamed_runs": rep, "replay_windowed_runs": win,
                       "uniform_random_cells_per_s": uni[1], "uniform_random_runs": uni,
                       "plotted_samples_per_s": plotted_per_s,
-                      "frac": plotted_per_s / rep[1],
+                      "frac": plotted_per_s / ceiling,
                       "frac_of_uniform_random": plotted_per_s / uni[1],
                       "note": "replay = bare REDs at the addresses this render scatters to (incl. K1e's "
-                              "tile scramble / row directory), 2048 threads/SM, 16 REDs in flight per "
-                              "thread: the scatter ceiling of this render. uniform random cells of the "
-                              "same buffer are a reference point only (an attractor can be L2-resident "
-                              "where uniform addresses stream from HBM)"}
+                              "tile scramble / row directory), 2048 threads/SM, nothing to wait for: the "
+                              "scatter ceiling of this render. streamed: the trace is read from memory (an "
+                              "L2 sector per 4 REDs); windowed: from shared memory, each window replayed "
+                              "many times. uniform random cells of the same buffer are a reference point "
+                              "only (an attractor can be L2-resident where uniform addresses stream from HBM)"}
         buf.zero_()
         self.barrier()
 

@@ -1907,9 +1907,10 @@ int ffr_cuda_atomic_roofline_ex(ffr_ctx *ctx, uint64_t n_atomics, int pattern, f
 {
     if (!ctx || !ms)
         return FFR_E_INVALID;
-    if (pattern != 0 && pattern != 1)
+    if (pattern < 0 || pattern > 2)
     {
-        ctx->err = "atomic_roofline: pattern must be 0 (uniform cells) or 1 (attractor replay)";
+        ctx->err = "atomic_roofline: pattern must be 0 (uniform cells), 1 (attractor replay, streamed trace) "
+                   "or 2 (attractor replay from shared-memory windows)";
         return FFR_E_INVALID;
     }
     DeviceState &ds = ctx->devs[0];
@@ -1943,7 +1944,9 @@ int ffr_cuda_atomic_roofline_ex(ffr_ctx *ctx, uint64_t n_atomics, int pattern, f
     /* record: the chains the render kernel keeps resident, n_atomics/chains samples each (an even
        number of chains: the replay reads entry pairs); statistics saved and restored */
     u64 chains = std::max<u64>(2,ffr_cuda_resident_chains(ctx)) & ~1ULL;
-    const u64 per_chain = std::max<u64>(1,n_atomics/chains);
+    /* pattern 2 replays windows many times over: a trace that fills them is enough */
+    const u64 want = pattern == 2 ? std::min<u64>(n_atomics,(u64)ds.sm_count*2*(96u*1024u/8u)) : n_atomics;
+    const u64 per_chain = std::max<u64>(1,(want + chains - 1)/chains);
     const u64 entries = chains*per_chain;
     DevTemp trace, saved;
     CK(trace.alloc(entries*sizeof(u64)));
@@ -1965,16 +1968,50 @@ int ffr_cuda_atomic_roofline_ex(ffr_ctx *ctx, uint64_t n_atomics, int pattern, f
     if (n_done)
         *n_done = after.s_plot - before.s_plot;
     CK(cudaMemcpyAsync(ds.d_stats,saved.p,sizeof(DevStats),cudaMemcpyDeviceToDevice,ds.stream));
-    CK(cudaEventRecord(ev.e0,ds.stream));
-    if (ctx->elem == 8)
-        atomic_replay_kernel<double><<<(unsigned)grid,FFR_REPLAY_TPB,0,ds.stream>>>((u64*)ds.buffer,(u64*)ds.d_acc,
-            trace.as<ulonglong2>(),entries/2,ctx->cellsz);
+    if (pattern == 2)
+    {
+        /* two blocks of 1024 threads per SM, each replaying its own 96 KiB window of the trace */
+        const uint32_t win = 96u*1024u/8u;
+        const size_t smem = (size_t)win*8;
+        const u64 wgrid = std::min<u64>((u64)ds.sm_count*2,(entries + win - 1)/win);
+        const u64 covered = std::min<u64>(entries,wgrid*win);
+        const uint32_t reps = (uint32_t)std::max<u64>(1,n_atomics/std::max<u64>(1,covered));
+        CK(cudaMemsetAsync(ds.d_scratch,0,sizeof(u64),ds.stream));
+        if (ctx->elem == 8)
+            CK(cudaFuncSetAttribute((const void*)atomic_replay_window_kernel<double>,
+                cudaFuncAttributeMaxDynamicSharedMemorySize,(int)smem));
+        else
+            CK(cudaFuncSetAttribute((const void*)atomic_replay_window_kernel<float>,
+                cudaFuncAttributeMaxDynamicSharedMemorySize,(int)smem));
+        CK(cudaEventRecord(ev.e0,ds.stream));
+        if (ctx->elem == 8)
+            atomic_replay_window_kernel<double><<<(unsigned)wgrid,1024,smem,ds.stream>>>((u64*)ds.buffer,(u64*)ds.d_acc,
+                trace.as<u64>(),entries,win,reps,ctx->cellsz,ds.d_scratch);
+        else
+            atomic_replay_window_kernel<float><<<(unsigned)wgrid,1024,smem,ds.stream>>>((unsigned int*)ds.buffer,
+                (unsigned int*)ds.d_acc,trace.as<u64>(),entries,win,reps,ctx->cellsz,ds.d_scratch);
+        ++ctx->launches;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ev.e1,ds.stream));
+        u64 n_red = 0;
+        CK(cudaMemcpyAsync(&n_red,ds.d_scratch,sizeof(u64),cudaMemcpyDeviceToHost,ds.stream));
+        CK(cudaStreamSynchronize(ds.stream));
+        if (n_done)
+            *n_done = n_red;
+    }
     else
-        atomic_replay_kernel<float><<<(unsigned)grid,FFR_REPLAY_TPB,0,ds.stream>>>((unsigned int*)ds.buffer,
-            (unsigned int*)ds.d_acc,trace.as<ulonglong2>(),entries/2,ctx->cellsz);
-    ++ctx->launches;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ev.e1,ds.stream));
+    {
+        CK(cudaEventRecord(ev.e0,ds.stream));
+        if (ctx->elem == 8)
+            atomic_replay_kernel<double><<<(unsigned)grid,FFR_REPLAY_TPB,0,ds.stream>>>((u64*)ds.buffer,(u64*)ds.d_acc,
+                trace.as<ulonglong2>(),entries/2,ctx->cellsz);
+        else
+            atomic_replay_kernel<float><<<(unsigned)grid,FFR_REPLAY_TPB,0,ds.stream>>>((unsigned int*)ds.buffer,
+                (unsigned int*)ds.d_acc,trace.as<ulonglong2>(),entries/2,ctx->cellsz);
+        ++ctx->launches;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ev.e1,ds.stream));
+    }
     CK(cudaEventSynchronize(ev.e1));
     CK(cudaEventElapsedTime(ms,ev.e0,ev.e1));
     /* what the replay put into K1e's tile goes where a render's would: the tile stays all zero

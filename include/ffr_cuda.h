@@ -238,7 +238,7 @@ enum ffr_scatter_mode
                                    ISAAC state (scatter strategies); what the library does
                                    instead for small/mid buffers is the L2-resident accumulation tile
                                    of the pure-affine kernel, chosen automatically */
-    FFR_SCATTER_TRACE = 5,      /* internal to ffr_cuda_atomic_roofline pattern 1 */
+    FFR_SCATTER_TRACE = 5,      /* internal to ffr_cuda_atomic_roofline patterns 1 and 2 */
     FFR_SCATTER_DISCARD = 4     /* diagnostic: iterate and count but issue no REDs (measures the
                                    compute-only rate for the roofline analysis; buffer untouched) */
 };
@@ -405,13 +405,20 @@ int ffr_cuda_iterate_points(ffr_ctx *ctx, int64_t xf_index, uint64_t n, const ui
 /* Test hook: first n words of the ISAAC-64 stream after setSeed(seed) (isaac.hpp:267-329) */
 int ffr_cuda_isaac_words(ffr_ctx *ctx, uint64_t seed, uint64_t n, uint64_t *out);
 
-/* Random-atomic microbenchmark: the measured scatter roofline. Issues
-   n_atomics REDs (1 u64 + color_dims f64 per cell) at pseudo-random cells of the
-   context's buffer with the render kernel's grid shape; returns elapsed ms (CUDA events).
-   pattern 0 = uniform cells; pattern 1 = replay of the flame's own attractor: a render of
-   resident_chains chains x (n_atomics / resident_chains) samples records every plotted cell
-   index, then the recorded stream is replayed as bare REDs (buffer contents are garbage
-   afterwards; statistics are restored). *n_done receives the number of cells actually hit. */
+/* Atomic-scatter microbenchmarks: the measured scatter roofline. Bare REDs
+   (1 count + color_dims colour sums per cell) issued from 2048 resident threads per SM with
+   nothing to wait for; returns elapsed ms (CUDA events) and in *n_done the cells actually hit.
+   pattern 0 = n_atomics uniformly random cells of the context's buffer (a reference point for
+     the memory system at this buffer size, not a ceiling for a render);
+   pattern 1 = replay of the flame's own scatter: a render of resident_chains chains x
+     (n_atomics / resident_chains) samples records the address every plotted sample was scattered
+     to (the buffer cell, or the cell of the pure-affine kernel's own accumulation tile after its
+     scramble / row directory), then the recorded stream is replayed, streamed from memory;
+   pattern 2 = the same replay from shared-memory windows of the trace, each replayed many times,
+     so that the timed loop issues nothing but REDs (the streamed trace costs an L2-resident
+     scatter a fifth of the L2's sector rate).
+   The better of patterns 1 and 2 is the scatter ceiling of that render. Buffer contents are
+   garbage afterwards; statistics are restored. */
 int ffr_cuda_atomic_roofline(ffr_ctx *ctx, uint64_t n_atomics, int pattern, float *ms);
 int ffr_cuda_atomic_roofline_ex(ffr_ctx *ctx, uint64_t n_atomics, int pattern, float *ms,
         uint64_t *n_done);
