@@ -185,9 +185,14 @@ def test_atomic_roofline_patterns(ffr, examples):
     before = r.fetch_stats()
     ms0, n0 = r.atomic_roofline(1 << 22, pattern=0)
     ms1, n1 = r.atomic_roofline(1 << 22, pattern=1)
-    assert ms0 > 0 and ms1 > 0
+    ms2, n2 = r.atomic_roofline(1 << 24, pattern=2)
+    assert ms0 > 0 and ms1 > 0 and ms2 > 0
     assert n0 >= (1 << 22) * 0.5
-    # the fern plots every sample, so the replay hits one cell per recorded sample
-    assert n1 == (max(1, (1 << 22) // r.resident_chains)) * r.resident_chains
+    # the fern plots every sample, so the streamed replay hits one cell per recorded sample:
+    # resident_chains chains x ceil(n / chains) samples
+    chains = r.resident_chains & ~1
+    assert n1 == chains * -(-(1 << 22) // chains)
+    # the windowed replay issues windows x repetitions REDs, about what was asked for
+    assert (1 << 23) <= n2 <= (1 << 24)
     assert r.fetch_stats() == before
     r.close()
