@@ -147,6 +147,7 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint2 s_ht[JNQ];         /* per queue: .x = head (claimed), .y = tail (reserved) */
     __shared__ int s_live;
+    __shared__ unsigned int s_xfc[JNX];               /* iterations executed per xform (flushed at 2^31) */
     W *rng_base = (W*)smem;                          /* randmem columns, 16 words per slot */
     W *st_a = rng_base + 16*JNS;                     /* randa, randb, randc, randcnt per slot */
     W *st_b = st_a + JNS;
@@ -174,12 +175,10 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
     const int chain_len = (int)prm.chain_len;                          /* host: < 2^31 */
     const int last_len = prm.last_len ? (int)prm.last_len : chain_len;
 
-    /* per-thread statistics (buffer_renderer.hpp:156-160), merged at kernel end (:232-246) */
-    u64 n_iter = 0, n_plot = 0;
-    unsigned int xfc[JNX];
-#pragma unroll
-    for (int j = 0; j < JNX; ++j)
-        xfc[j] = 0;
+    /* per-thread statistics (buffer_renderer.hpp:156-160), merged at kernel end (:232-246).
+       ++s_iter and ++xf_dist[id] (:171-172) are counted once per popped chunk, below; s_iter is
+       their sum. */
+    u64 n_plot = 0;
     T pmin[JD], pmax[JD];
 #pragma unroll
     for (int i = 0; i < JD; ++i)
@@ -194,6 +193,8 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
     {
         s_ht[tid] = make_uint2(0u,0u);
     }
+    if (tid < JNX)
+        s_xfc[tid] = 0u;
     if (tid == 0)
         s_live = JNS;
     __syncthreads();
@@ -384,6 +385,28 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
 
         unsigned newkey = JKEY_NONE;
         bool fresh = false;
+        int it = -1;
+        if (q != JQ_GEN)
+        {
+            /* ++s_iter, ++xf_dist[xf_id] (buffer_renderer.hpp:171-172): the whole chunk runs xform q,
+               so one popc per chunk instead of JNX compare-adds per lane and iteration */
+            if (act)
+                it = s_it[slot];
+            const unsigned cm = __ballot_sync(0xffffffffu,it >= 0);
+            if (lane == 0 && cm)
+            {
+                const unsigned add = (unsigned)__popc(cm);
+                const unsigned old = atomicAdd(&s_xfc[q],add);
+                /* rare: the 32-bit block counter crossed 2^31 with this add (exactly one warp sees
+                   the crossing): move 2^31 of it to the global 64-bit counters */
+                if (old < 0x80000000u && old + add >= 0x80000000u)
+                {
+                    atomicSub(&s_xfc[q],0x80000000u);
+                    atomicAdd(&prm.stats->xf_dist[q],0x80000000ULL);
+                    atomicAdd(&prm.stats->s_iter,0x80000000ULL);
+                }
+            }
+        }
         if (q == JQ_GEN)
         {
             /* the slot's select draw found randcnt == 0: next(), isaac.hpp:321-329 */
@@ -401,18 +424,11 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
                 s_keys[slot] = go.keys;
                 STORE_ABC(rng,slot);
                 st_n[slot] = (W)15;
-                if (s_it[slot] >= 0)
-                {
-#pragma unroll
-                    for (int j = 0; j < JNX; ++j)
-                        xfc[j] += (newkey == (unsigned)j) ? 1u : 0u;
-                }
             }
         }
         else if (act)
         {
             const unsigned k = q;
-            const int it = s_it[slot];
             const unsigned chain = s_chain[slot];
             T p[JD], pf[JD];
             T c[JRC], cf[JRC];
@@ -461,7 +477,6 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
                         cf[i] = c[i];
                 }
                 /* _render_batch body, buffer_renderer.hpp:171-229 */
-                ++n_iter;
                 bool bad = false;
 #pragma unroll
                 for (int i = 0; i < JD; ++i)
@@ -505,11 +520,20 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
                 }
                 if (!gone)
                 {
+                    /* extremes of p (:188-194): after the first samples a new extreme is rare, so one
+                       combined test and a branch instead of 4*D selects */
+                    bool ext = false;
 #pragma unroll
-                    for (int i = 0; i < JD; ++i) /* :188-194 */
+                    for (int i = 0; i < JD; ++i)
+                        ext |= (p[i] < pmin[i]) | (p[i] > pmax[i]);
+                    if (ext)
                     {
-                        pmin[i] = (p[i] < pmin[i]) ? p[i] : pmin[i];
-                        pmax[i] = (p[i] > pmax[i]) ? p[i] : pmax[i];
+#pragma unroll
+                        for (int i = 0; i < JD; ++i)
+                        {
+                            pmin[i] = (p[i] < pmin[i]) ? p[i] : pmin[i];
+                            pmax[i] = (p[i] > pmax[i]) ? p[i] : pmax[i];
+                        }
                     }
                     /* inclusive bounds on pf (render_iterator.hpp:72-79); NaN is out (Q4) */
                     if (jit_inb(pf))
@@ -566,12 +590,6 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
                 {
                     --rng.cnt;
                     newkey = (unsigned)(keys >> (4*rng.cnt)) & 15u;
-                    if (nit >= 0)
-                    {
-#pragma unroll
-                        for (int j = 0; j < JNX; ++j)
-                            xfc[j] += (newkey == (unsigned)j) ? 1u : 0u;
-                    }
                 }
                 else
                     newkey = JQ_GEN;   /* a converged warp runs gen() for 32 such slots */
@@ -599,11 +617,7 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
     {
-        n_iter += __shfl_xor_sync(0xffffffffu,n_iter,o);
         n_plot += __shfl_xor_sync(0xffffffffu,n_plot,o);
-#pragma unroll
-        for (int j = 0; j < JNX; ++j)
-            xfc[j] += __shfl_xor_sync(0xffffffffu,xfc[j],o);
 #pragma unroll
         for (int i = 0; i < JD; ++i)
         {
@@ -615,16 +629,18 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
     }
     if (lane == 0)
     {
-        if (n_iter) atomicAdd(&prm.stats->s_iter,n_iter);
         if (n_plot) atomicAdd(&prm.stats->s_plot,n_plot);
-#pragma unroll
-        for (int j = 0; j < JNX; ++j)
-            if (xfc[j]) atomicAdd(&prm.stats->xf_dist[j],(u64)xfc[j]);
 #pragma unroll
         for (int i = 0; i < JD; ++i)
         {
             atomicMin(&prm.stats->pt_min[i],f64_to_ordered((double)pmin[i]));
             atomicMax(&prm.stats->pt_max[i],f64_to_ordered((double)pmax[i]));
         }
+    }
+    __syncthreads();
+    if (tid < JNX && s_xfc[tid])
+    {
+        atomicAdd(&prm.stats->xf_dist[tid],(u64)s_xfc[tid]);
+        atomicAdd(&prm.stats->s_iter,(u64)s_xfc[tid]);
     }
 }

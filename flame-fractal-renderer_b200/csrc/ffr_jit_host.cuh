@@ -302,6 +302,10 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
        just served instead measured -0.4 %); FFR_JIT_ROT_STATIC=0 rotates */
     if (!(getenv("FFR_JIT_ROT_STATIC") && *getenv("FFR_JIT_ROT_STATIC") == '0'))
         h << "#define JROT_STATIC 1\n";
+    /* experiment switch (never default): let ptxas contract a*b+c into FMAs. Breaks the exactness
+       contract, so only meaningful for flames that are compared statistically anyway */
+    if (getenv("FFR_JIT_FMAD") && *getenv("FFR_JIT_FMAD") == '1')
+        h << "/*FFR_NVRTC_FMAD*/\n";
     if (cfg.async)
         h << "#define JRSL_SMEM " << (fl->uses_rng ? 1 : 0) << "\n"
           << (fl->uses_rng ? "" : "#define FFR_RSL_LOAD(p) __ldcg(p)\n");
@@ -1003,7 +1007,8 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
         err = "nvrtcCreateProgram failed";
         return false;
     }
-    const char *opts[] = {"--gpu-architecture=sm_100a","-fmad=false","-std=c++17","-lineinfo","-default-device",
+    const bool fmad = src.find("/*FFR_NVRTC_FMAD*/") != std::string::npos;
+    const char *opts[] = {"--gpu-architecture=sm_100a",fmad ? "-fmad=true" : "-fmad=false","-std=c++17","-lineinfo","-default-device",
         "--ptxas-options=-v",inc_opt.c_str()};
     const nvrtcResult rc = a.CompileProgram(prog,inc_opt.empty() ? 6 : 7,opts);
     std::string log;
