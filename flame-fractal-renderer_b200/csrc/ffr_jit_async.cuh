@@ -140,7 +140,11 @@ __device__ __noinline__ unsigned long long jit_keys_from_rsl(const JW *rcol)
     return keys;
 }
 
-extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const RenderParams prm)
+/* MODES = false: plain RED scatter. MODES = true: prm.scatter_mode honoured (warp-aggregated,
+   discard, trace), used by the scatter diagnostics and the attractor-replay roofline -- a second
+   entry point, so that the render kernel proper carries neither the tests nor the code. */
+template <bool MODES>
+__device__ __forceinline__ void jit_render_async(const RenderParams &prm)
 {
     typedef JT T;
     typedef JW W;
@@ -168,9 +172,9 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     W *__restrict__ buffer = (W*)prm.buffer;
-    const bool warp_agg = prm.scatter_mode == FFR_SCATTER_WARP_AGG;
-    const bool discard = prm.scatter_mode == FFR_SCATTER_DISCARD || prm.scatter_mode == FFR_SCATTER_TRACE;
-    u64 *__restrict__ trace = prm.scatter_mode == FFR_SCATTER_TRACE ? prm.trace : nullptr;
+    const bool warp_agg = MODES && prm.scatter_mode == FFR_SCATTER_WARP_AGG;
+    const bool discard = MODES && (prm.scatter_mode == FFR_SCATTER_DISCARD || prm.scatter_mode == FFR_SCATTER_TRACE);
+    u64 *__restrict__ trace = (MODES && prm.scatter_mode == FFR_SCATTER_TRACE) ? prm.trace : nullptr;
     const unsigned int chain_count = (unsigned int)prm.chain_count;   /* host: < 2^31 per launch */
     const int chain_len = (int)prm.chain_len;                          /* host: < 2^31 */
     const int last_len = prm.last_len ? (int)prm.last_len : chain_len;
@@ -540,10 +544,10 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
                     {
                         ++n_plot;
                         const u64 bi = jit_index(pf); /* :202-209 */
-                        if (trace)
+                        if (MODES && trace)
                             trace[(u64)it*prm.chain_count + chain] = bi;
                         W *cell = buffer + bi*(1 + JR);
-                        if (warp_agg)
+                        if (MODES && warp_agg)
                         {
                             const unsigned pe = __match_any_sync(__activemask(),bi);
                             if ((int)(__ffs(pe) - 1) == lane)
@@ -643,4 +647,14 @@ extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const Re
         atomicAdd(&prm.stats->xf_dist[tid],(u64)s_xfc[tid]);
         atomicAdd(&prm.stats->s_iter,(u64)s_xfc[tid]);
     }
+}
+
+extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const RenderParams prm)
+{
+    jit_render_async<false>(prm);
+}
+
+extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render_modes(const RenderParams prm)
+{
+    jit_render_async<true>(prm);
 }

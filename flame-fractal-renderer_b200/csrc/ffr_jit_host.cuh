@@ -306,6 +306,8 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
        contract, so only meaningful for flames that are compared statistically anyway */
     if (getenv("FFR_JIT_FMAD") && *getenv("FFR_JIT_FMAD") == '1')
         h << "/*FFR_NVRTC_FMAD*/\n";
+    if (cfg.async && !(getenv("FFR_JIT_GEN_ROLLED") && *getenv("FFR_JIT_GEN_ROLLED") == '0'))
+        h << "#define FFR_GEN_ROLLED 1\n";
     if (cfg.async)
         h << "#define JRSL_SMEM " << (fl->uses_rng ? 1 : 0) << "\n"
           << (fl->uses_rng ? "" : "#define FFR_RSL_LOAD(p) __ldcg(p)\n");
