@@ -24,11 +24,19 @@ step:
    launch drains.
 
 Queues are multi-producer/multi-consumer rings of slot numbers: producers reserve positions
-with one warp-aggregated atomicAdd on the tail and then write the entries; consumers claim a
+with one warp-aggregated atomic add on the tail and then write the entries; consumers claim a
 range with a CAS on the head and wait for each claimed entry to become valid (a producer that
 reserved a position writes it a few instructions later and waits for nothing in between).
 At most JNS entries are ever reserved-and-unread over all queues (one per slot), so a ring of
-JCAP >= JNS entries cannot overrun.
+JCAP >= JNS entries cannot overrun. An entry carries the parity of its lap around the ring in
+bit 15 (position / JCAP mod 2): a consumer of position p waits until the entry shows p's lap,
+so nobody ever has to mark an entry as consumed (every reserved position is written exactly
+once per lap, hence the previous lap's value always has the other parity).
+Memory model: the entry is published with st.release.cta and read with ld.acquire.cta, which
+orders the slot's state (plain shared-memory stores before the push, plain loads after the pop)
+across the two warps; head and tail are relaxed atomics. JQ_ACQREL = 0 compiles the entry
+accesses as volatile instead (what round 1 shipped: correct on this hardware, where one thread's
+shared-memory stores are performed in order, but outside the PTX memory model).
 
 Which warp advances a chain, and in which order chains interleave, changes neither a chain's
 stream nor its arithmetic: histogram counts and statistics equal K1/K1b/K1c bit for bit
@@ -42,14 +50,57 @@ lists, plus JCAP.
 
 #include "ffr_params.cuh"
 
+#ifndef JQ_ACQREL
+#define JQ_ACQREL 1
+#endif
 #define JKEY_NONE 0xffu
 #define JRC (JR > 0 ? JR : 1)
 #define JNQ (JNX + 1)            /* xform queues + the gen() queue */
 #define JQ_GEN JNX
-#define JEMPTY 0xffffu
 #define JMASK (JCAP - 1)          /* JCAP: ring capacity, the power of two >= JNS */
+#define JLAP(pos) ((((pos) & (unsigned)JCAP) != 0u) ? 0x8000u : 0u)   /* lap parity of a position */
 #define JABORT_WATCHDOG 0x100u
 typedef Real<JT>::word JW;
+
+/* queue primitives on 32-bit shared-window addresses (no generic-address arithmetic, no branch
+   around the one-lane atomics: they are predicated instructions) */
+__device__ __forceinline__ void jq_publish(unsigned addr, unsigned v)
+{
+#if JQ_ACQREL
+    asm volatile("st.release.cta.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory");
+#else
+    asm volatile("st.volatile.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory");
+#endif
+}
+
+__device__ __forceinline__ unsigned jq_peek(unsigned addr)
+{
+    unsigned short v;
+#if JQ_ACQREL
+    asm volatile("ld.acquire.cta.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+#else
+    asm volatile("ld.volatile.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+#endif
+    return v;
+}
+
+/* old = CAS(addr, cmp, val) on the lanes where p is set; other lanes get ~cmp */
+__device__ __forceinline__ unsigned jq_cas_pred(unsigned addr, unsigned cmp, unsigned val, bool p)
+{
+    unsigned old = ~cmp;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %4, 0;\n\t@q atom.relaxed.cta.shared.cas.b32 %0, [%1], %2, %3;\n\t}"
+        : "+r"(old) : "r"(addr), "r"(cmp), "r"(val), "r"((unsigned)p) : "memory");
+    return old;
+}
+
+/* old = fetch-and-add on the lanes where p is set; other lanes get 0 */
+__device__ __forceinline__ unsigned jq_add_pred(unsigned addr, unsigned val, bool p)
+{
+    unsigned old = 0;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q atom.relaxed.cta.shared.add.u32 %0, [%1], %2;\n\t}"
+        : "+r"(old) : "r"(addr), "r"(val), "r"((unsigned)p) : "memory");
+    return old;
+}
 
 struct JitChain
 {
@@ -151,7 +202,7 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint2 s_ht[JNQ];         /* per queue: .x = head (claimed), .y = tail (reserved) */
     __shared__ int s_live;
-    __shared__ unsigned int s_xfc[JNX];               /* iterations executed per xform (flushed at 2^31) */
+    __shared__ unsigned long long s_wxf[(JTPB/32)*JNX];   /* per warp: iterations executed per xform */
     W *rng_base = (W*)smem;                          /* randmem columns, 16 words per slot */
     W *st_a = rng_base + 16*JNS;                     /* randa, randb, randc, randcnt per slot */
     W *st_b = st_a + JNS;
@@ -192,13 +243,16 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
     }
 
     for (int i = tid; i < JNQ*JCAP; i += JTPB)
-        ring[i] = (unsigned short)JEMPTY;
+        ring[i] = (unsigned short)0x8000u;     /* the lap before the first: valid for nobody */
     if (tid < JNQ)
     {
         s_ht[tid] = make_uint2(0u,0u);
     }
-    if (tid < JNX)
-        s_xfc[tid] = 0u;
+    for (int i = tid; i < (JTPB/32)*JNX; i += JTPB)
+        s_wxf[i] = 0ULL;
+    const unsigned ht_s = (unsigned)__cvta_generic_to_shared(&s_ht[0]);
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    unsigned long long *my_wxf = s_wxf + (tid >> 5)*JNX;
     if (tid == 0)
         s_live = JNS;
     __syncthreads();
@@ -255,21 +309,20 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
             const unsigned peers_ = __match_any_sync(0xffffffffu,(key)); \
             const unsigned rank_ = __popc(peers_ & ((1u << lane) - 1u)); \
             const int leader_ = __ffs(peers_) - 1; \
-            unsigned pos_ = 0; \
-            if ((key) < JNQ && rank_ == 0) \
-                pos_ = atomicAdd(&s_ht[key].y,(unsigned)__popc(peers_)); \
-            pos_ = __shfl_sync(0xffffffffu,pos_,leader_); \
-            /* The slot's state must be visible before its queue entry. Shared-memory stores of \
-               one thread are performed in program order, so the compiler is all that has to be \
-               kept from reordering. NO memory fence anywhere in this kernel: with a MEMBAR in \
-               the code ptxas turns every scatter RED into an ATOMG whose (discarded) return \
-               value the warp then waits for -- measured 2x on the colour flames. Generator \
-               words that other warps may read go to shared memory when the flame has drawing \
-               variations (JRSL_SMEM); otherwise the global scratch is only read by cold paths \
-               many steps after the gen() that wrote it, with L1-bypassing loads. */ \
-            asm volatile("" ::: "memory"); \
-            if ((key) < JNQ) \
-                *(volatile unsigned short*)&ring[(key)*JCAP + ((pos_ + rank_) & JMASK)] = (unsigned short)(slot); \
+            const bool queued_ = (key) < JNQ; \
+            unsigned pos_ = jq_add_pred(ht_s + 8u*(key) + 4u,(unsigned)__popc(peers_),queued_ && rank_ == 0); \
+            pos_ = __shfl_sync(0xffffffffu,pos_,leader_) + rank_; \
+            /* The slot's state (plain shared-memory stores above) must be visible before its \
+               queue entry: the entry is a release store (JQ_ACQREL), which costs one \
+               MEMBAR.ALL.CTA and leaves the scatter a RED -- a fence.acq_rel or a wider membar \
+               anywhere in this kernel makes ptxas turn every scatter RED into an ATOMG whose \
+               (discarded) return value the warp then waits for, measured 2x on the colour \
+               flames. Generator words that other warps may read go to shared memory when the \
+               flame has drawing variations (JRSL_SMEM); otherwise the global scratch is only \
+               read by cold paths many steps after the gen() that wrote it, with L1-bypassing \
+               loads. */ \
+            if (queued_) \
+                jq_publish(ring_s + 2u*((key)*JCAP + (pos_ & JMASK)),(unsigned)(slot) | JLAP(pos_)); \
         } \
     } while (0)
 
@@ -323,9 +376,7 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
                 const unsigned hexp = __shfl_sync(0xffffffffu,hd,(int)bl);
                 unsigned want = __shfl_sync(0xffffffffu,av,(int)bl);
                 want = want < 32u ? want : 32u;
-                unsigned ok = 0;
-                if (lane == 0)
-                    ok = atomicCAS(&s_ht[bl].x,hexp,hexp + want) == hexp ? 1u : 0u;
+                unsigned ok = jq_cas_pred(ht_s + 8u*bl,hexp,hexp + want,lane == 0) == hexp ? 1u : 0u;
                 ok = __shfl_sync(0xffffffffu,ok,0);
                 if (ok)
                 {
@@ -372,20 +423,20 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
         unsigned slot = 0;
         if (act)
         {
-            volatile unsigned short *e = &ring[q*JCAP + ((h0 + lane) & JMASK)];
-            unsigned v = *e;
+            const unsigned pos = h0 + (unsigned)lane;
+            const unsigned ea = ring_s + 2u*(q*JCAP + (pos & JMASK));
+            const unsigned lap = JLAP(pos);
+            unsigned v = jq_peek(ea);
             unsigned long long w = 0;
-            while (v == JEMPTY && ++w < (1ULL << 28))
-                v = *e;
-            if (v == JEMPTY)
+            while ((v & 0x8000u) != lap && ++w < (1ULL << 28))
+                v = jq_peek(ea);
+            if ((v & 0x8000u) != lap)
             {
                 atomicOr((unsigned int*)&prm.stats->abort,JABORT_WATCHDOG);
                 v = 0;
             }
-            *e = (unsigned short)JEMPTY;
-            slot = v;
+            slot = v & 0x7fffu;
         }
-        asm volatile("" ::: "memory");   /* queue entry before the slot's state (see the push) */
 
         unsigned newkey = JKEY_NONE;
         bool fresh = false;
@@ -397,19 +448,8 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
             if (act)
                 it = s_it[slot];
             const unsigned cm = __ballot_sync(0xffffffffu,it >= 0);
-            if (lane == 0 && cm)
-            {
-                const unsigned add = (unsigned)__popc(cm);
-                const unsigned old = atomicAdd(&s_xfc[q],add);
-                /* rare: the 32-bit block counter crossed 2^31 with this add (exactly one warp sees
-                   the crossing): move 2^31 of it to the global 64-bit counters */
-                if (old < 0x80000000u && old + add >= 0x80000000u)
-                {
-                    atomicSub(&s_xfc[q],0x80000000u);
-                    atomicAdd(&prm.stats->xf_dist[q],0x80000000ULL);
-                    atomicAdd(&prm.stats->s_iter,0x80000000ULL);
-                }
-            }
+            if (lane == 0)
+                my_wxf[q] += (unsigned long long)__popc(cm);
         }
         if (q == JQ_GEN)
         {
@@ -642,10 +682,16 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
         }
     }
     __syncthreads();
-    if (tid < JNX && s_xfc[tid])
+    if (tid < JNX)
     {
-        atomicAdd(&prm.stats->xf_dist[tid],(u64)s_xfc[tid]);
-        atomicAdd(&prm.stats->s_iter,(u64)s_xfc[tid]);
+        u64 n = 0;
+        for (int w = 0; w < JTPB/32; ++w)
+            n += s_wxf[w*JNX + tid];
+        if (n)
+        {
+            atomicAdd(&prm.stats->xf_dist[tid],n);
+            atomicAdd(&prm.stats->s_iter,n);
+        }
     }
 }
 

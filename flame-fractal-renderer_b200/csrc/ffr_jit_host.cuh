@@ -308,6 +308,10 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
         h << "/*FFR_NVRTC_FMAD*/\n";
     if (cfg.async && !(getenv("FFR_JIT_GEN_ROLLED") && *getenv("FFR_JIT_GEN_ROLLED") == '0'))
         h << "#define FFR_GEN_ROLLED 1\n";
+    /* K1d: queue entries as release stores / acquire loads (default); FFR_JIT_ACQREL=0 compiles the
+       round-1 form (volatile accesses, no MEMBAR.CTA) for A/B measurements */
+    if (cfg.async && getenv("FFR_JIT_ACQREL") && *getenv("FFR_JIT_ACQREL") == '0')
+        h << "#define JQ_ACQREL 0\n";
     if (cfg.async)
         h << "#define JRSL_SMEM " << (fl->uses_rng ? 1 : 0) << "\n"
           << (fl->uses_rng ? "" : "#define FFR_RSL_LOAD(p) __ldcg(p)\n");

@@ -146,3 +146,35 @@ def test_few_very_long_chains_do_not_trip_the_watchdog(ffr, po, examples):
     for k in ("s_iter", "s_plot", "xf_dist", "n_bad", "pt_min", "pt_max"):
         assert st[k] == ost[k], k
     assert np.array_equal(got, want)
+
+
+def test_queue_soak_many_launches_bit_exact(ffr, examples):
+    """Soak of K1d's slot queues (release/acquire ring entries, lap parity, predicated one-lane
+    atomics): >= 100 launches of ragged chain ranges, 1e11 samples in all (FFR_SOAK_SAMPLES
+    overrides; profiles/ holds a 1e12 run), on an IEEE-only flame (spherical: class ii), so every
+    count and statistic must equal the ahead-of-time kernel's bit for bit. A lost or duplicated
+    slot, or a slot whose state was read before it was visible, changes counts."""
+    import os
+    total = int(float(os.environ.get("FFR_SOAK_SAMPLES", "1e11")))
+    launches, L = 100, 4096
+    per = total // launches // L
+    fl = ffr.Flame(examples.example_json("flam3_test_1", size=[512, 512]))
+    res = []
+    for jit in (ffr.JIT_ON, ffr.JIT_OFF):
+        r = ffr.BufferRenderer(fl, jit=jit)
+        if jit == ffr.JIT_ON:
+            assert "K1d queue-scheduled kernel" in r.jit_info["message"]
+        first = 0
+        for k in range(launches):
+            count = per + (k * 37) % 101          # ragged: a different remainder every launch
+            r.render_chains_async(first, count, L, last_len=(k * 13) % L, base_seed=3, bv_limit=1 << 60)
+            first += count
+        r.sync()
+        st = r.fetch_stats()
+        res.append((r.read_buffer(), st))
+        r.close()
+    (b1, s1), (b0, s0) = res
+    assert s1["s_iter"] >= total * 0.99
+    for k in ("s_iter", "s_plot", "xf_dist", "n_bad", "pt_min", "pt_max"):
+        assert s1[k] == s0[k], k
+    assert np.array_equal(b1, b0)
