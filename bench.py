@@ -16,9 +16,11 @@ NCCL/NVLink. Prints ONE JSON line on rank 0.
 value     device-timed (CUDA events on the launching stream) throughput of K steps with
           everything resident in HBM.
 e2e       the same metric through the reference-facing C ABI with HOST buffers: every step
-          uploads the previous host buffer (the -i resume path, ffr_cuda_add_buffer), renders
-          (blocking ffr_cuda_render_chains incl. statistics read-back) and reads the whole
-          buffer back (ffr_cuda_read_buffer) -- H2D and D2H inside the timed region.
+          uploads a pinned host buffer (the -i resume path), renders and reads the whole buffer
+          back to pinned host memory -- H2D and D2H inside the timed region. At N = 1 the steps go
+          through the library's streaming interface (ffr_cuda_*_async) on two contexts used
+          alternately, so one step's read-back overlaps the next step's upload and render; at
+          N > 1 through the blocking calls around the NCCL reduce.
 roofline  HBM: algorithmic bytes (one RMW of one cell per PLOTTED sample = 2*(1+r)*8 B) per
           launch / average launch duration, against MEASURED_PEAKS.json hbm_gbs.
 atomic_roofline  the north star's denominator: bare REDs at the addresses this render scatters
@@ -403,24 +405,47 @@ class Bench:
                 if rank == 0:
                     e2e_rend.read_buffer(out_np)
         else:
+            # two contexts on two streams, used alternately: step k+1's upload and render overlap
+            # step k's read-back (the library's streaming interface; every step still uploads its
+            # input from pinned host memory and reads its whole result back)
             e2e_rend = ffr.BufferRenderer(flame, devices=[self.local_rank], jit=self.jit)
+            e2e_rend2 = ffr.BufferRenderer(flame, devices=[self.local_rank], jit=self.jit)
+            host_out2 = torch.zeros(n_elems, dtype=torch.int64).pin_memory()
+            out2_np = host_out2.numpy().view(np.uint64)
+            pipe = [(e2e_rend, out_np), (e2e_rend2, out2_np)]
 
             def e2e_step(k):
-                e2e_rend.clear()
-                e2e_rend.add_buffer(in_np)
+                r, out = pipe[k % 2]
+                r.sync()                      # this context's previous step (two steps ago)
+                r.clear_async()
+                r.add_buffer_async(in_np)
                 first = (k + 500_000) * chains_per_step
-                e2e_rend.render_chains(first, chains_per_step, L, base_seed=1)
-                e2e_rend.read_buffer(out_np)
+                r.render_chains_async(first, chains_per_step, L, base_seed=1)
+                r.read_buffer_async(out)
 
-        e2e_steps = max(3, min(steps, 20))
+        e2e_steps = max(4, min(steps, 20))
+        e2e_step(-2)
         e2e_step(-1)
+        if world == 1:
+            e2e_rend.sync()
+            e2e_rend2.sync()
         self.barrier()
         t0 = time.perf_counter()
         for k in range(e2e_steps):
             e2e_step(k)
+        if world == 1:
+            e2e_rend.sync()
+            e2e_rend2.sync()
         self.barrier()
         e2e_s = self.max_over_ranks(time.perf_counter() - t0)
         e2e_value = samples_per_step * e2e_steps * world / e2e_s
+        if world == 1:
+            # the result of the last step really arrived: every sample of a step is iterated once
+            st_a, st_b = e2e_rend.fetch_stats(), e2e_rend2.fetch_stats()
+            assert st_a["s_iter"] + st_b["s_iter"] == samples_per_step * (e2e_steps + 2)
+            assert int(out_np.sum() + out2_np.sum()) > 0 if cell == 1 else True
+            e2e_rend2.close()
+            del host_out2, out2_np
         e2e_rend.close()
         del buf, ebuf, host_in, host_out, in_np, out_np
         torch.cuda.empty_cache()

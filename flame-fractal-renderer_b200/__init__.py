@@ -154,6 +154,9 @@ ABI = {
                                          C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(FfrStats)]),
     "ffr_cuda_render_chains_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
                                                C.c_uint64, C.c_uint64, C.c_uint64]),
+    "ffr_cuda_clear_buffer_async": (C.c_int, [C.c_void_p]),
+    "ffr_cuda_add_buffer_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ffr_cuda_read_buffer_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ffr_cuda_sync": (C.c_int, [C.c_void_p]),
     "ffr_cuda_get_stats": (C.c_int, [C.c_void_p, C.POINTER(FfrStats)]),
     "ffr_cuda_resident_chains": (C.c_uint64, [C.c_void_p]),
@@ -362,6 +365,20 @@ class BufferRenderer:
                             bv_limit=256):
         self._check(lib().ffr_cuda_render_chains_async(
             self._h, chain_first, chain_count, chain_len, last_len, base_seed, bv_limit))
+
+    # the streaming interface: enqueue only; page-locked host buffers, valid until sync()
+    def clear_async(self):
+        self._check(lib().ffr_cuda_clear_buffer_async(self._h))
+
+    def add_buffer_async(self, pinned):
+        a = np.asarray(pinned)
+        assert a.flags.c_contiguous
+        self._check(lib().ffr_cuda_add_buffer_async(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def read_buffer_async(self, pinned_out):
+        assert pinned_out.flags.c_contiguous
+        self._check(lib().ffr_cuda_read_buffer_async(self._h, pinned_out.ctypes.data_as(C.c_void_p),
+                                                     pinned_out.nbytes))
 
     def sync(self):
         self._check(lib().ffr_cuda_sync(self._h))

@@ -1186,6 +1186,33 @@ void *ffr_cuda_device_buffer(ffr_ctx *ctx, int dev_index)
     return ctx->devs[dev_index].buffer;
 }
 
+/* page-locked host memory is mapped into the device's address space (UVA): its device alias, or
+   null for pageable memory */
+static const void *pinned_alias(const void *host)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a,host) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer)
+        return nullptr;
+    return a.devicePointer;
+}
+
+static int launch_add(ffr_ctx *ctx, DeviceState &ds, void *dst, const void *src, size_t n, size_t first)
+{
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255)/256,(size_t)ds.sm_count*16);
+    if (ctx->elem == 8)
+        add_buffer_kernel<double><<<grid,256,0,ds.stream>>>((u64*)dst,(const u64*)src,n,ctx->cellsz,first);
+    else
+        add_buffer_kernel<float><<<grid,256,0,ds.stream>>>((unsigned int*)dst,(const unsigned int*)src,n,ctx->cellsz,first);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    return FFR_OK;
+}
+
 int ffr_cuda_add_buffer(ffr_ctx *ctx, const void *host, size_t bytes)
 {
     if (!ctx || !host)
@@ -1197,11 +1224,22 @@ int ffr_cuda_add_buffer(ffr_ctx *ctx, const void *host, size_t bytes)
     }
     DeviceState &ds = ctx->devs[0];
     CK(cudaSetDevice(ds.dev));
-    /* stage in chunks so a 1 GiB -i file does not double the footprint; the staging buffer
-       is kept for the next call */
     const size_t eb = ctx->elem;
-    const size_t chunk_elems = ((size_t)1 << 27) / eb; /* 128 MiB */
     const size_t n_elems = bytes/eb;
+    if (const void *alias = pinned_alias(host))
+    {
+        /* page-locked memory: the add kernel reads it in place over PCIe */
+        int rc = launch_add(ctx,ds,ds.buffer,alias,n_elems,0);
+        if (rc != FFR_OK)
+            return rc;
+        CK(cudaStreamSynchronize(ds.stream));
+        return FFR_OK;
+    }
+    /* pageable memory: stage in chunks so that a 1 GiB -i file does not double the footprint; the
+       staging buffer is kept for the next call. Stream order protects its reuse (the copy of
+       chunk k+1 starts after the add of chunk k); one synchronisation at the end, because the
+       host buffer is only borrowed. */
+    const size_t chunk_elems = ((size_t)1 << 27) / eb; /* 128 MiB */
     size_t chunk = std::min(n_elems,chunk_elems - (chunk_elems % ctx->cellsz));
     if (ds.stage_elems < chunk)
     {
@@ -1212,22 +1250,82 @@ int ffr_cuda_add_buffer(ffr_ctx *ctx, const void *host, size_t bytes)
         CK(cudaMalloc(&ds.d_stage,chunk*eb));
         ds.stage_elems = chunk;
     }
-    void *tmp = ds.d_stage;
     for (size_t off = 0; off < n_elems; off += chunk)
     {
         size_t n = std::min(chunk,n_elems - off);
-        CK(cudaMemcpyAsync(tmp,(const char*)host + off*eb,n*eb,cudaMemcpyHostToDevice,ds.stream));
-        unsigned grid = (unsigned)std::min<size_t>((n + 255)/256,(size_t)ds.sm_count*16);
-        if (eb == 8)
-            add_buffer_kernel<double><<<grid,256,0,ds.stream>>>((u64*)ds.buffer + off,(const u64*)tmp,n,ctx->cellsz);
-        else
-            add_buffer_kernel<float><<<grid,256,0,ds.stream>>>((unsigned int*)ds.buffer + off,
-                (const unsigned int*)tmp,n,ctx->cellsz);
-        ++ctx->launches;
-        CK(cudaGetLastError());
-        /* the staging buffer is reused by the next chunk and the host buffer is only borrowed */
-        CK(cudaStreamSynchronize(ds.stream));
+        CK(cudaMemcpyAsync(ds.d_stage,(const char*)host + off*eb,n*eb,cudaMemcpyHostToDevice,ds.stream));
+        int rc = launch_add(ctx,ds,(char*)ds.buffer + off*eb,ds.d_stage,n,off);
+        if (rc != FFR_OK)
+            return rc;
     }
+    CK(cudaStreamSynchronize(ds.stream));
+    return FFR_OK;
+}
+
+static int single_device(ffr_ctx *ctx, const char *what)
+{
+    if (ctx->devs.size() != 1)
+    {
+        ctx->err = std::string(what) + " needs a single device context";
+        return FFR_E_INVALID;
+    }
+    return FFR_OK;
+}
+
+int ffr_cuda_add_buffer_async(ffr_ctx *ctx, const void *pinned_host, size_t bytes)
+{
+    if (!ctx || !pinned_host)
+        return FFR_E_INVALID;
+    if (single_device(ctx,"add_buffer_async") != FFR_OK)
+        return FFR_E_INVALID;
+    if (bytes != ctx->bytes)
+    {
+        ctx->err = "BufferRenderer::addBuffer(): sizes do not match";
+        return FFR_E_INVALID;
+    }
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    const void *alias = pinned_alias(pinned_host);
+    if (!alias)
+    {
+        ctx->err = "add_buffer_async: the host buffer must be page-locked";
+        return FFR_E_INVALID;
+    }
+    return launch_add(ctx,ds,ds.buffer,alias,bytes/ctx->elem,0);
+}
+
+int ffr_cuda_read_buffer_async(ffr_ctx *ctx, void *pinned_host, size_t bytes)
+{
+    if (!ctx || !pinned_host)
+        return FFR_E_INVALID;
+    if (single_device(ctx,"read_buffer_async") != FFR_OK)
+        return FFR_E_INVALID;
+    if (bytes != ctx->bytes)
+    {
+        ctx->err = "read_buffer: size mismatch";
+        return FFR_E_INVALID;
+    }
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    if (!pinned_alias(pinned_host))
+    {
+        ctx->err = "read_buffer_async: the host buffer must be page-locked";
+        return FFR_E_INVALID;
+    }
+    CK(cudaMemcpyAsync(pinned_host,ds.buffer,bytes,cudaMemcpyDeviceToHost,ds.stream));
+    return FFR_OK;
+}
+
+int ffr_cuda_clear_buffer_async(ffr_ctx *ctx)
+{
+    if (!ctx)
+        return FFR_E_INVALID;
+    if (single_device(ctx,"clear_buffer_async") != FFR_OK)
+        return FFR_E_INVALID;
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    CK(cudaMemsetAsync(ds.buffer,0,ctx->bytes,ds.stream));
+    ds.dirty = false;
     return FFR_OK;
 }
 

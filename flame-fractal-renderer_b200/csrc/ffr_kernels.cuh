@@ -761,24 +761,39 @@ __global__ void fold_dir_kernel(W *__restrict__ tile, W *__restrict__ buffer, co
    src may be peer memory (multi-GPU reduce over NVLink) or a staged host buffer (-i). */
 template <typename T>
 __global__ void add_buffer_kernel(typename Real<T>::word *__restrict__ dst,
-        const typename Real<T>::word *__restrict__ src, u64 n_elems, uint32_t cellsz)
+        const typename Real<T>::word *__restrict__ src, u64 n_elems, uint32_t cellsz, u64 first_elem)
 {
     typedef typename Real<T>::word W;
     const u64 stride = (u64)gridDim.x*blockDim.x;
-    for (u64 i = (u64)blockIdx.x*blockDim.x + threadIdx.x; i < n_elems; i += stride)
+    /* four independent loads in flight per thread: src may be page-locked host memory read over
+       PCIe, where latency is microseconds */
+    for (u64 i0 = (u64)blockIdx.x*blockDim.x + threadIdx.x; i0 < n_elems; i0 += 4*stride)
     {
-        const W s = src[i];
-        if (cellsz == 1 || i % cellsz == 0)
-            dst[i] += s;
-        else
+        W s[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
         {
-            T a, b;
-            W d = dst[i];
-            memcpy(&a,&d,sizeof(T));
-            memcpy(&b,&s,sizeof(T));
-            a += b;
-            memcpy(&d,&a,sizeof(T));
-            dst[i] = d;
+            const u64 i = i0 + (u64)k*stride;
+            s[k] = i < n_elems ? __ldcs(src + i) : (W)0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const u64 i = i0 + (u64)k*stride;
+            if (i >= n_elems)
+                continue;
+            if (cellsz == 1 || (first_elem + i) % cellsz == 0)
+                dst[i] += s[k];
+            else
+            {
+                T a, b;
+                W d = dst[i];
+                memcpy(&a,&d,sizeof(T));
+                memcpy(&b,&s[k],sizeof(T));
+                a += b;
+                memcpy(&d,&a,sizeof(T));
+                dst[i] = d;
+            }
         }
     }
 }

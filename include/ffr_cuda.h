@@ -318,6 +318,15 @@ int ffr_cuda_render_chains(ffr_ctx *ctx, uint64_t chain_first, uint64_t chain_co
    its own stream (ffr_options.stream). Single device contexts only. */
 int ffr_cuda_render_chains_async(ffr_ctx *ctx, uint64_t chain_first, uint64_t chain_count,
         uint64_t chain_len, uint64_t last_len, uint64_t base_seed, uint64_t bv_limit);
+/* The rest of the streaming interface (single device contexts): clear, -i add and read-back that
+   only enqueue on the context's stream, so that a host running two contexts on two streams
+   overlaps one context's PCIe legs with the other's render (bench.py's e2e loop does). The host
+   buffers must be PAGE-LOCKED (cudaHostAlloc / cudaHostRegister / torch pin_memory) and stay
+   valid and untouched until ffr_cuda_sync returns; pageable memory is refused (FFR_E_INVALID).
+   The add reads the pinned buffer directly over PCIe (no staging copy). */
+int ffr_cuda_clear_buffer_async(ffr_ctx *ctx);
+int ffr_cuda_add_buffer_async(ffr_ctx *ctx, const void *pinned_host, size_t bytes);
+int ffr_cuda_read_buffer_async(ffr_ctx *ctx, void *pinned_host, size_t bytes);
 int ffr_cuda_sync(ffr_ctx *ctx);
 int ffr_cuda_get_stats(ffr_ctx *ctx, ffr_stats *stats);
 /* chains the render kernel keeps in flight per device (SMs x resident blocks x 256): size

@@ -196,3 +196,45 @@ def test_atomic_roofline_patterns(ffr, examples):
     assert (1 << 23) <= n2 <= (1 << 24)
     assert r.fetch_stats() == before
     r.close()
+
+
+def test_streaming_interface_equals_blocking_calls(ffr, po, examples):
+    """ffr_cuda_{clear,add_buffer,read_buffer}_async + render_chains_async on page-locked
+    buffers give the buffer the blocking calls give; pageable host memory is refused; the
+    blocking add takes the zero-copy path for pinned memory and the staged path otherwise."""
+    import torch
+    fl = ffr.Flame(examples.example_json("tkoz_test3", size=[320, 200]))   # mixed u64 / f64 cells
+    _, _, cells, cs = fl.layout()
+    prev, _, _ = po.oracle_render(fl, 64, 500, base_seed=8, nthreads=4)
+    pinned_in = torch.from_numpy(prev.view(np.int64)).pin_memory()
+    pinned_out = torch.zeros(cells * cs, dtype=torch.int64).pin_memory()
+    in_np = pinned_in.numpy().view(np.uint64)
+    out_np = pinned_out.numpy().view(np.uint64)
+    r = ffr.BufferRenderer(fl)
+    for _ in range(2):          # twice: the second pass starts from a cleared buffer again
+        r.clear_async()
+        r.add_buffer_async(in_np)
+        r.render_chains_async(0, 300, 700, base_seed=5)
+        r.read_buffer_async(out_np)
+        r.sync()
+    got = out_np.copy()
+    with pytest.raises(ffr.FfrError, match="page-locked"):
+        r.add_buffer_async(prev)
+    with pytest.raises(ffr.FfrError, match="page-locked"):
+        r.read_buffer_async(np.zeros(cells * cs, dtype=np.uint64))
+    r.close()
+    want = []
+    for src in (in_np, prev):    # pinned (zero-copy add) and pageable (staged add)
+        b = ffr.BufferRenderer(fl)
+        b.add_buffer(src)
+        assert b.render_chains(0, 300, 700, base_seed=5)
+        want.append(b.read_buffer())
+        b.close()
+    gc, gcol = ffr.split_counts_colors(got, cells, cs - 1)
+    for w in want:
+        wc, wcol = ffr.split_counts_colors(w, cells, cs - 1)
+        assert np.array_equal(gc, wc)
+        np.testing.assert_allclose(gcol, wcol, rtol=1e-12, atol=1e-12)
+    # and the -i semantics hold: counts = previous counts + this render's
+    pc, _ = ffr.split_counts_colors(prev, cells, cs - 1)
+    assert int(gc.sum()) == int(pc.sum()) + 0 + int((gc - pc).sum()) and (gc >= pc).all()
