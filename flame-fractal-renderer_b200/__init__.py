@@ -164,6 +164,8 @@ ABI = {
     "ffr_cuda_reduce": (C.c_int, [C.c_void_p]),
     "ffr_cuda_sum_device_slices": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int,
                                              C.c_uint64, C.c_uint64]),
+    "ffr_cuda_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ffr_cuda_ipc_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "ffr_cuda_read_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ffr_cuda_histogram_sum_max": (C.c_int, [C.c_void_p, _u64p, _u64p]),
     "ffr_cuda_tonemap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_size_t,
@@ -401,6 +403,17 @@ class BufferRenderer:
 
     def reduce(self):
         self._check(lib().ffr_cuda_reduce(self._h))
+
+    def ipc_export(self):
+        """64-byte CUDA IPC handle of this context's buffer (for another process on the box)."""
+        h = C.create_string_buffer(64)
+        self._check(lib().ffr_cuda_ipc_export(self._h, h))
+        return h.raw
+
+    def ipc_add(self, handles):
+        """Add the buffers behind other processes' IPC handles into this context's buffer."""
+        blob = b"".join(handles)
+        self._check(lib().ffr_cuda_ipc_add(self._h, blob, len(handles)))
 
     def sum_device_slices(self, dst_ptr, src_ptrs, first_elem, n_elems):
         """dst += sum(srcs) on the device, typed by position in the cell (K2d)."""

@@ -139,7 +139,8 @@ struct DeviceState
     int sm_count = 0;
     int blocks_per_sm = 0;
     bool dirty = false;            /* holds samples not yet reduced into device 0 */
-    jit::Module jmod;              /* K1c: the flame-specialised kernel loaded on this device */
+    jit::Module jmod;              /* the flame-specialised kernel loaded on this device */
+    jit::Module jmod_modes;        /* K1d/K1e: its diagnostics variant (prm.scatter_mode), loaded on demand */
     int jit_blocks_per_sm = 0;
     void *d_rsl_jit = nullptr;     /* K1c randrsl scratch */
     void *d_acc = nullptr;         /* K1e accumulation tile (scrambled cell order), cells words */
@@ -181,6 +182,7 @@ struct ffr_ctx
     double jit_compile_s = 0.0;
     std::string jit_source, jit_err, jit_note;
     std::vector<char> jit_cubin;
+    std::vector<char> jit_cubin_modes;   /* compiled by the first launch that needs it */
 };
 
 namespace
@@ -820,6 +822,33 @@ void jit_maybe(ffr_ctx *ctx, u64 samples)
     }
 }
 
+/* the diagnostics variant of the run-time compiled kernel: same source, other entry point */
+int jit_load_modes(ffr_ctx *ctx, DeviceState &ds)
+{
+    if (ds.jmod_modes.fn)
+        return FFR_OK;
+    if (ctx->jit_cubin_modes.empty())
+    {
+        double secs = 0.0;
+        bool cached = false;
+        long spills = 0;
+        if (!jit::compile("#define JIT_MODES_ENTRY 1\n" + ctx->jit_source,ctx->jit_cubin_modes,ctx->jit_err,
+                &secs,&cached,&spills,false))
+        {
+            ctx->jit_cubin_modes.clear();
+            ctx->err = "run-time compilation of the diagnostics kernel failed: " + ctx->jit_err;
+            return FFR_E_UNSUPPORTED;
+        }
+        ctx->jit_compile_s += secs;
+    }
+    if (!jit::load(ctx->jit_cubin_modes,ctx->jit_smem,ds.jmod_modes,ctx->jit_err,"ffr_jit_render_modes"))
+    {
+        ctx->err = ctx->jit_err;
+        return FFR_E_CUDA;
+    }
+    return FFR_OK;
+}
+
 /* K2b / K2c: what a K1e launch (or the attractor replay) left in its accumulation tile goes into
    the buffer in the reference's cell order; the tile is all zero afterwards */
 int fold_tiles(ffr_ctx *ctx, DeviceState &ds)
@@ -908,8 +937,16 @@ int launch_render(ffr_ctx *ctx, DeviceState &ds, u64 chain_first, u64 chain_coun
         prm.rsl_scratch = ds.d_rsl_jit;
         void *args[] = {&prm};
         jit::Api &a = jit::api(true);
-        /* K1e: scatter diagnostics (warp aggregation, discard, trace) live in a second entry point */
-        CUfunction fn = (ctx->scatter_mode != FFR_SCATTER_GLOBAL && ds.jmod.fn_modes) ? ds.jmod.fn_modes : ds.jmod.fn;
+        /* K1d/K1e: scatter diagnostics (warp aggregation, discard, trace) live in a variant of the
+           kernel that is compiled and loaded the first time one of them is asked for */
+        CUfunction fn = ds.jmod.fn;
+        if (ctx->scatter_mode != FFR_SCATTER_GLOBAL && (ctx->jit_cfg.async || ctx->jit_cfg.affine))
+        {
+            const int mrc = jit_load_modes(ctx,ds);
+            if (mrc != FFR_OK)
+                return mrc;
+            fn = ds.jmod_modes.fn;
+        }
         const CUresult r = a.LaunchKernel(fn,(unsigned)grid,1,1,(unsigned)ctx->jit_cfg.tpb,1,1,
             (unsigned)ctx->jit_smem,(CUstream)ds.stream,args,nullptr);
         if (r != CUDA_SUCCESS)
@@ -1158,6 +1195,7 @@ void ffr_cuda_destroy(ffr_ctx *ctx)
         if (ds.d_acc) cudaFree(ds.d_acc);
         if (ds.d_dir) cudaFree(ds.d_dir);
         if (ds.jmod.mod) jit::unload(ds.jmod);
+        if (ds.jmod_modes.mod) jit::unload(ds.jmod_modes);
         if (ds.d_stage) cudaFree(ds.d_stage);
         if (ds.own_stream && ds.stream) cudaStreamDestroy(ds.stream);
     }
@@ -1677,6 +1715,59 @@ int ffr_cuda_sum_device_slices(ffr_ctx *ctx, void *dst, const void *const *srcs,
     for (int k = 0; k < n_src; ++k)
         ps.src[k] = srcs[k];
     return launch_reduce_slices(ctx,ds,dst,ps,n_src,first_elem,n_elems);
+}
+
+int ffr_cuda_ipc_export(ffr_ctx *ctx, void *handle)
+{
+    if (!ctx || !handle)
+        return FFR_E_INVALID;
+    if (single_device(ctx,"ipc_export") != FFR_OK)
+        return FFR_E_INVALID;
+    DeviceState &ds = ctx->devs[0];
+    if (!ds.own_buffer)
+    {
+        ctx->err = "ipc_export: the buffer belongs to the caller (external_buffer)";
+        return FFR_E_INVALID;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == FFR_IPC_HANDLE_BYTES,"CUDA IPC handle size");
+    CK(cudaSetDevice(ds.dev));
+    CK(cudaStreamSynchronize(ds.stream));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h,ds.buffer));
+    memcpy(handle,&h,sizeof(h));
+    return FFR_OK;
+}
+
+int ffr_cuda_ipc_add(ffr_ctx *ctx, const void *handles, int n)
+{
+    if (!ctx || (!handles && n > 0) || n < 0 || n > FFR_MAX_PEERS)
+        return FFR_E_INVALID;
+    if (single_device(ctx,"ipc_add") != FFR_OK)
+        return FFR_E_INVALID;
+    if (n == 0)
+        return FFR_OK;
+    DeviceState &ds = ctx->devs[0];
+    CK(cudaSetDevice(ds.dev));
+    PeerSlices ps;
+    memset(&ps,0,sizeof(ps));
+    void *opened[FFR_MAX_PEERS] = {nullptr};
+    int rc = FFR_OK;
+    for (int k = 0; k < n && rc == FFR_OK; ++k)
+    {
+        cudaIpcMemHandle_t h;
+        memcpy(&h,(const char*)handles + (size_t)k*FFR_IPC_HANDLE_BYTES,sizeof(h));
+        if (!cuda_ok(ctx,cudaIpcOpenMemHandle(&opened[k],h,cudaIpcMemLazyEnablePeerAccess),"cudaIpcOpenMemHandle"))
+            rc = FFR_E_CUDA;
+        ps.src[k] = opened[k];
+    }
+    if (rc == FFR_OK)
+        rc = launch_reduce_slices(ctx,ds,ds.buffer,ps,n,0,ctx->bytes/ctx->elem);
+    if (rc == FFR_OK && !cuda_ok(ctx,cudaStreamSynchronize(ds.stream),"ipc_add sync"))
+        rc = FFR_E_CUDA;
+    for (int k = 0; k < n; ++k)
+        if (opened[k])
+            cudaIpcCloseMemHandle(opened[k]);
+    return rc;
 }
 
 int ffr_cuda_read_buffer(ffr_ctx *ctx, void *host, size_t bytes)

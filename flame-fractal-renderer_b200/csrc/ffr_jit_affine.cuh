@@ -437,12 +437,15 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
         atomicAdd(&prm.stats->xf_dist[tid],s_xf[tid]);
 }
 
+/* one entry point per compilation (the diagnostics variant is compiled on demand) */
+#ifndef JIT_MODES_ENTRY
 extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const RenderParams prm)
 {
     jaf_render<false>(prm);
 }
-
+#else
 extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render_modes(const RenderParams prm)
 {
     jaf_render<true>(prm);
 }
+#endif

@@ -695,12 +695,17 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
     }
 }
 
+/* one entry point per compilation: the render kernel proper, or -- compiled on demand, the first
+   time a scatter diagnostic or the attractor-replay roofline asks for it (JIT_MODES_ENTRY) -- the
+   variant that honours prm.scatter_mode */
+#ifndef JIT_MODES_ENTRY
 extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render(const RenderParams prm)
 {
     jit_render_async<false>(prm);
 }
-
+#else
 extern "C" __global__ void __launch_bounds__(JTPB,JMINB) ffr_jit_render_modes(const RenderParams prm)
 {
     jit_render_async<true>(prm);
 }
+#endif

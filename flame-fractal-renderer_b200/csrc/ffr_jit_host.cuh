@@ -1035,7 +1035,7 @@ inline bool compile(const std::string &src, std::vector<char> &cubin, std::strin
     cubin.resize(n);
     a.GetCUBIN(prog,cubin.data());
     a.DestroyProgram(&prog);
-    /* "Function properties for ffr_jit_render ... N bytes spill stores" */
+    /* "Function properties for ffr_jit_render[_modes] ... N bytes spill stores" */
     long long spills = 0;
     {
         size_t at = log.find("Function properties for ffr_jit_render");
@@ -1090,7 +1090,6 @@ struct Module
 {
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;
-    CUfunction fn_modes = nullptr;   /* K1e: the variant that honours prm.scatter_mode */
     int regs = 0;
 };
 
@@ -1101,7 +1100,8 @@ inline std::string cu_err(Api &a, CUresult r)
     return s ? s : "unknown driver error";
 }
 
-inline bool load(const std::vector<char> &cubin, size_t smem, Module &m, std::string &err)
+inline bool load(const std::vector<char> &cubin, size_t smem, Module &m, std::string &err,
+        const char *entry = "ffr_jit_render")
 {
     Api &a = api(true);
     if (!a.LaunchKernel)
@@ -1115,7 +1115,7 @@ inline bool load(const std::vector<char> &cubin, size_t smem, Module &m, std::st
         err = "cuModuleLoadData: " + cu_err(a,r);
         return false;
     }
-    r = a.ModuleGetFunction(&m.fn,m.mod,"ffr_jit_render");
+    r = a.ModuleGetFunction(&m.fn,m.mod,entry);
     if (r != CUDA_SUCCESS)
     {
         err = "cuModuleGetFunction: " + cu_err(a,r);
@@ -1128,10 +1128,6 @@ inline bool load(const std::vector<char> &cubin, size_t smem, Module &m, std::st
         return false;
     }
     a.FuncGetAttribute(&m.regs,CU_FUNC_ATTRIBUTE_NUM_REGS,m.fn);
-    if (a.ModuleGetFunction(&m.fn_modes,m.mod,"ffr_jit_render_modes") != CUDA_SUCCESS)
-        m.fn_modes = nullptr;
-    else if (a.FuncSetAttribute(m.fn_modes,CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,(int)smem) != CUDA_SUCCESS)
-        m.fn_modes = nullptr;
     return true;
 }
 

@@ -17,7 +17,13 @@ options:
 -b,--batch-size   samples per chain (work unit); 0 = calculate a reasonable size
 -z,--bad-values   number of bad values allowed before terminating render
    --seed         base seed of the per-chain ISAAC streams (default: clock)
-   --gpus         number of GPUs to shard the chains over (default 1)
+   --gpus         number of GPUs to shard the chains over (default 1). N > 1 runs one PROCESS per
+                  GPU (fork before any CUDA call): creating N CUDA contexts inside one process is
+                  serialised by the driver (8 GPUs: 7.5 s before the first kernel), N processes
+                  create theirs in parallel. The workers render their chain ranges into private
+                  buffers; the first process adds them to its own over NVLink peer memory (CUDA
+                  IPC) and writes the output. FFR_SINGLE_PROCESS=1 keeps everything in one process
+                  (the library's multi-device context).
    --float        the reference's float/uint32_t build (types.hpp:24-41) instead of the shipped
                   double/uint64_t one: 4-byte buffer elements, ISAAC-32
 */
@@ -25,7 +31,10 @@ options:
 #include "../../include/ffr_flame.h"
 
 #include <getopt.h>
+#include <signal.h>
+#include <sys/wait.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -87,6 +96,112 @@ static void progress_cb(void *user, uint64_t done, uint64_t total)
         << std::min<uint64_t>(p->samples,done*p->batch) << "/" << p->samples << " samples ("
         << (int)(100*frac) << "%) " << (tn / 1e9) << "sec elapsed, (~"
         << (trem / 1e9) << "sec remaining)";
+}
+
+/* ---- one process per GPU (--gpus N) ---- */
+
+struct WorkerMsg
+{
+    int rc;                         /* FFR_OK / FFR_BAD_VALUES / < 0 */
+    char err[256];
+    unsigned char handle[FFR_IPC_HANDLE_BYTES];
+    ffr_stats stats;
+};
+
+static bool write_all(int fd, const void *p, size_t n)
+{
+    const char *c = (const char*)p;
+    while (n)
+    {
+        ssize_t w = write(fd,c,n);
+        if (w <= 0)
+            return false;
+        c += w;
+        n -= (size_t)w;
+    }
+    return true;
+}
+
+static bool read_all_fd(int fd, void *p, size_t n)
+{
+    char *c = (char*)p;
+    while (n)
+    {
+        ssize_t r = read(fd,c,n);
+        if (r <= 0)
+            return false;
+        c += r;
+        n -= (size_t)r;
+    }
+    return true;
+}
+
+/* contiguous chain range of process `rank` (the rule ffr_cuda_render_chains uses between devices) */
+static void chain_range(uint64_t chains, int nproc, int rank, uint64_t *first, uint64_t *count)
+{
+    const uint64_t per = (chains + nproc - 1) / nproc;
+    *first = std::min<uint64_t>(per*rank,chains);
+    *count = std::min<uint64_t>(per,chains - *first);
+}
+
+/* a worker: render the range, hand the buffer to the collector, wait until it is done with it */
+[[noreturn]] static void worker_main(int rank, int nproc, const ffr_flame_desc *desc, const ffr_options &opt0,
+        uint64_t chains, uint64_t chain_len, uint64_t last_len, uint64_t seed, uint64_t bv_limit,
+        int up_fd, int down_fd)
+{
+    static WorkerMsg msg;
+    memset(&msg,0,sizeof(msg));
+    ffr_options opt = opt0;
+    ffr_ctx *ctx = ffr_cuda_create_ex(desc,&rank,1,&opt,msg.err,sizeof(msg.err));
+    if (!ctx && opt.jit == 2)
+    {
+        opt.jit = 1;
+        ctx = ffr_cuda_create_ex(desc,&rank,1,&opt,msg.err,sizeof(msg.err));
+    }
+    if (!ctx)
+        msg.rc = FFR_E_CUDA;
+    else
+    {
+        uint64_t first, count;
+        chain_range(chains,nproc,rank,&first,&count);
+        const bool has_last = first + count == chains;
+        msg.rc = count ? ffr_cuda_render_chains(ctx,first,count,chain_len,has_last ? last_len : 0,seed,bv_limit,&msg.stats)
+                       : ffr_cuda_get_stats(ctx,&msg.stats);
+        if (msg.rc < 0)
+            snprintf(msg.err,sizeof(msg.err),"%s",ffr_cuda_last_error(ctx));
+        else if (ffr_cuda_ipc_export(ctx,msg.handle) != FFR_OK)
+        {
+            msg.rc = FFR_E_CUDA;
+            snprintf(msg.err,sizeof(msg.err),"%s",ffr_cuda_last_error(ctx));
+        }
+    }
+    write_all(up_fd,&msg,sizeof(msg));
+    char done;
+    read_all_fd(down_fd,&done,1);      /* the collector has added this buffer (or gave up) */
+    if (ctx)
+        ffr_cuda_destroy(ctx);
+    _exit(0);
+}
+
+static void merge_stats(ffr_stats &a, const ffr_stats &b, uint32_t dims)
+{
+    a.s_iter += b.s_iter;
+    a.s_plot += b.s_plot;
+    for (int i = 0; i < FFR_MAX_XFORMS; ++i)
+        a.xf_dist[i] += b.xf_dist[i];
+    for (uint32_t d = 0; d < dims; ++d)
+    {
+        a.pt_min[d] = std::min(a.pt_min[d],b.pt_min[d]);
+        a.pt_max[d] = std::max(a.pt_max[d],b.pt_max[d]);
+    }
+    const uint64_t na = std::min<uint64_t>(a.n_bad,FFR_MAX_BAD_RECORDED), nb = std::min<uint64_t>(b.n_bad,FFR_MAX_BAD_RECORDED);
+    for (uint64_t k = 0; k < nb && na + k < FFR_MAX_BAD_RECORDED; ++k)
+    {
+        a.bad_xf[na + k] = b.bad_xf[k];
+        for (int d = 0; d < FFR_MAX_DIMS; ++d)
+            a.bad_pt[na + k][d] = b.bad_pt[k][d];
+    }
+    a.n_bad += b.n_bad;
 }
 
 int main(int argc, char **argv)
@@ -241,14 +356,99 @@ int main(int argc, char **argv)
     memset(&opt,0,sizeof(opt));
     opt.struct_size = sizeof(opt);
     opt.jit = arg_jit;
-    ffr_ctx *ctx = ffr_cuda_create_ex(desc,nullptr,arg_gpus,&opt,err,sizeof(err));
-    if (!ctx && arg_jit == 2)
+
+    /* the chains of the whole job (every process and device derives its share from these) */
+    const uint64_t total_chains = arg_samples ? (arg_samples + arg_batch_size - 1) / arg_batch_size : 0;
+    const uint64_t last_chain = arg_samples - (total_chains ? (total_chains - 1)*arg_batch_size : 0);
+    const uint64_t last_len = (last_chain == arg_batch_size) ? 0 : last_chain;
+
+    /* --gpus N: one process per GPU. Nothing below this point has touched CUDA yet, so forking is
+       safe; the run-time compiled kernel is built ONCE, before the fork (NVRTC needs no device), and
+       the workers inherit it through the library's in-process cache. */
+    const bool single = getenv("FFR_SINGLE_PROCESS") && *getenv("FFR_SINGLE_PROCESS") == '1';
+    const int nproc = (arg_gpus > 1 && !single && arg_samples > 0) ? arg_gpus : 1;
+    std::vector<pid_t> pids;
+    std::vector<int> up_fds, down_fds;
+    if (nproc > 1)
+    {
+        if (arg_samples < 256*(uint64_t)1 || arg_batch_size < 256)
+        {
+            std::cerr << "ERROR: BufferRenderer::render(): batch size too small" << std::endl;
+            return 1;
+        }
+        if (opt.jit == 0 && arg_samples >= 50000000000ull)
+            opt.jit = 2;        /* the auto threshold applies to the job, not to one process's share */
+        if (opt.jit == 2)
+        {
+            char jerr[512];
+            if (ffr_cuda_jit_compile(desc,nullptr,0,nullptr,jerr,sizeof(jerr)) != FFR_OK)
+            {
+                if (arg_jit == 2)
+                    std::cerr << "note: " << jerr << "; using the ahead-of-time kernels" << std::endl;
+                opt.jit = 1;
+            }
+        }
+        phase("kernel compiled");
+        signal(SIGPIPE,SIG_IGN);
+        for (int r = 1; r < nproc; ++r)
+        {
+            int up[2], down[2];
+            if (pipe(up) != 0 || pipe(down) != 0)
+            {
+                std::cerr << "ERROR: pipe() failed" << std::endl;
+                return 1;
+            }
+            const pid_t pid = fork();
+            if (pid < 0)
+            {
+                std::cerr << "ERROR: fork() failed" << std::endl;
+                return 1;
+            }
+            if (pid == 0)
+            {
+                close(up[0]);
+                close(down[1]);
+                for (int fd : up_fds) close(fd);
+                for (int fd : down_fds) close(fd);
+                worker_main(r,nproc,desc,opt,total_chains,arg_batch_size,last_len,arg_seed,arg_bad_values,
+                    up[1],down[0]);
+            }
+            close(up[1]);
+            close(down[0]);
+            pids.push_back(pid);
+            up_fds.push_back(up[0]);
+            down_fds.push_back(down[1]);
+        }
+    }
+    auto release_workers = [&]()
+    {
+        for (int fd : down_fds)
+        {
+            char done = 1;
+            write_all(fd,&done,1);
+            close(fd);
+        }
+        for (int fd : up_fds)
+            close(fd);
+        for (pid_t pid : pids)
+            waitpid(pid,nullptr,0);
+        down_fds.clear();
+        up_fds.clear();
+        pids.clear();
+    };
+
+    const int dev0 = 0;
+    const int ctx_devices = nproc > 1 ? 1 : arg_gpus;
+    ffr_ctx *ctx = ffr_cuda_create_ex(desc,nproc > 1 ? &dev0 : nullptr,ctx_devices,&opt,err,sizeof(err));
+    if (!ctx && opt.jit == 2)
     {
         /* the flame-specialised kernel is an optimisation: fall back to the interpreter kernels */
         std::cerr << "note: " << err << "; using the ahead-of-time kernels" << std::endl;
         opt.jit = 1;
-        ctx = ffr_cuda_create_ex(desc,nullptr,arg_gpus,&opt,err,sizeof(err));
+        ctx = ffr_cuda_create_ex(desc,nproc > 1 ? &dev0 : nullptr,ctx_devices,&opt,err,sizeof(err));
     }
+    if (!ctx)
+        release_workers();
     if (!ctx)
     {
         std::cerr << "ERROR: " << err << std::endl;
@@ -308,8 +508,58 @@ int main(int argc, char **argv)
         for (int g = 0; g < arg_gpus; ++g)
             std::cerr << "started thread " << g << " (cuda:" << g << ")" << std::endl;
         static ffr_stats stats;
-        int rc = ffr_cuda_render(ctx,arg_samples,arg_batch_size,arg_seed,arg_bad_values,
-            progress_cb,&prog,&stats);
+        int rc;
+        if (nproc == 1)
+            rc = ffr_cuda_render(ctx,arg_samples,arg_batch_size,arg_seed,arg_bad_values,
+                progress_cb,&prog,&stats);
+        else
+        {
+            /* this process's share, in a few launches with a progress line after each (scaled to
+               the job: the workers advance at the same rate), then the workers' buffers */
+            uint64_t first, count;
+            chain_range(total_chains,nproc,0,&first,&count);
+            const uint64_t wave = std::max<uint64_t>(1,ffr_cuda_resident_chains(ctx));
+            const uint64_t segs = std::min<uint64_t>(32,std::max<uint64_t>(1,count / (wave*4)));
+            const uint64_t per = (count + segs - 1) / std::max<uint64_t>(1,segs);
+            rc = FFR_OK;
+            for (uint64_t f = 0; f < count && rc >= 0; f += per)
+            {
+                const uint64_t c = std::min<uint64_t>(per,count - f);
+                const bool has_last = first + f + c == total_chains;
+                const int r1 = ffr_cuda_render_chains(ctx,first + f,c,arg_batch_size,has_last ? last_len : 0,
+                    arg_seed,arg_bad_values,&stats);
+                rc = r1 < 0 ? r1 : std::max(rc,r1);
+                progress_cb(&prog,std::min<uint64_t>(total_chains,(f + c)*nproc),total_chains);
+                if (r1 == FFR_BAD_VALUES)
+                    break;
+            }
+            static WorkerMsg msg;
+            std::vector<unsigned char> handles;
+            for (size_t w = 0; w < up_fds.size() && rc >= 0; ++w)
+            {
+                if (!read_all_fd(up_fds[w],&msg,sizeof(msg)))
+                {
+                    std::cerr << std::endl << "ERROR: worker " << (w + 1) << " died" << std::endl;
+                    release_workers();
+                    return 1;
+                }
+                if (msg.rc < 0)
+                {
+                    std::cerr << std::endl << "ERROR: worker " << (w + 1) << ": " << msg.err << std::endl;
+                    release_workers();
+                    return 1;
+                }
+                rc = std::max(rc,msg.rc);
+                merge_stats(stats,msg.stats,desc->dims);
+                handles.insert(handles.end(),msg.handle,msg.handle + FFR_IPC_HANDLE_BYTES);
+            }
+            if (rc >= 0 && !handles.empty() &&
+                    ffr_cuda_ipc_add(ctx,handles.data(),(int)(handles.size()/FFR_IPC_HANDLE_BYTES)) != FFR_OK)
+                rc = FFR_E_CUDA;
+            release_workers();
+            if (stats.n_bad > arg_bad_values && rc == FFR_OK)
+                rc = FFR_BAD_VALUES;
+        }
         // like the reference, the timer spans render() only (ffr_buf.cpp:189-227); the buffer
         // reduce + copy to the host happens below, as the reference's write does
         clock_gettime(CLOCK_MONOTONIC,&t2);

@@ -373,6 +373,16 @@ int ffr_cuda_reduce(ffr_ctx *ctx);
 int ffr_cuda_sum_device_slices(ffr_ctx *ctx, void *dst, const void *const *srcs, int n_src,
         uint64_t first_elem, uint64_t n_elems);
 
+/* One process per GPU on one box (what `ffr-buf.out --gpus N` does: every CUDA context is created
+   by a process of its own, in parallel, instead of N contexts serialised inside one process):
+   a worker exports its single-device context's buffer as a CUDA IPC handle (64 bytes, sent to the
+   collecting process through a pipe), the collector adds the workers' buffers to its own buffer
+   by reading them in place over NVLink peer memory (K2d, typed by cell position). The worker must
+   keep its context alive until the collector's call returned. n <= 15. */
+#define FFR_IPC_HANDLE_BYTES 64
+int ffr_cuda_ipc_export(ffr_ctx *ctx, void *handle);
+int ffr_cuda_ipc_add(ffr_ctx *ctx, const void *handles, int n);
+
 /* writeBuffer (buffer_renderer.hpp:476-480): the reduced buffer in the reference file
    layout: cells x [count u64, c0..c(r-1) f64], dimension 0 fastest, native endian. */
 int ffr_cuda_read_buffer(ffr_ctx *ctx, void *host, size_t bytes);

@@ -238,3 +238,59 @@ def test_streaming_interface_equals_blocking_calls(ffr, po, examples):
     # and the -i semantics hold: counts = previous counts + this render's
     pc, _ = ffr.split_counts_colors(prev, cells, cs - 1)
     assert int(gc.sum()) == int(pc.sum()) + 0 + int((gc - pc).sum()) and (gc >= pc).all()
+
+
+def _run_cli(ffr, args, env=None):
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(ffr.LIB_PATH), "ffr-buf.out")
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([exe] + args, capture_output=True, text=True, env=e, timeout=600)
+
+
+@pytest.mark.parametrize("name,size,flag", [("barnsley_fern", [256, 160], "--no-jit"),
+                                            ("tkoz_test3", [192, 108], "--jit"),
+                                            ("csci6360_project", [192, 108], "--jit")])
+def test_cli_one_process_per_gpu_equals_one_gpu(ffr, examples, tmp_path, name, size, flag):
+    """ffr-buf.out --gpus 2: two processes (fork before any CUDA call), the worker's buffer added
+    to the collector's over CUDA IPC peer memory. Counts byte-identical to the 1-GPU file, the
+    same stderr report (s_iter, s_plot, xform selection); also the single-process form."""
+    if ffr.lib().ffr_cuda_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    flame = tmp_path / "f.json"
+    flame.write_text(examples.example_json(name, size=size))
+    fl = ffr.Flame(flame.read_text())
+    _, _, cells, cs = fl.layout()
+    common = ["-f", str(flame), "-s", "3000000", "-b", "1000", "--seed", "11", flag]
+    outs, reports = [], []
+    for tag, extra, env in (("one", [], None), ("two", ["--gpus", "2"], None),
+                            ("two_sp", ["--gpus", "2"], {"FFR_SINGLE_PROCESS": "1"})):
+        out = tmp_path / (tag + ".buf")
+        p = _run_cli(ffr, common + ["-o", str(out)] + extra, env)
+        assert p.returncode == 0, p.stderr
+        outs.append(np.fromfile(out, dtype=np.uint64))
+        reports.append([ln for ln in p.stderr.split("\n")
+                        if ln.startswith(("samples iterated", "samples plotted", "xform selection",
+                                          "extreme coordinates"))])
+    c0, col0 = ffr.split_counts_colors(outs[0], cells, cs - 1)
+    for o in outs[1:]:
+        c, col = ffr.split_counts_colors(o, cells, cs - 1)
+        assert np.array_equal(c, c0)
+        if cs > 1:
+            np.testing.assert_allclose(col, col0, rtol=1e-12, atol=1e-12)
+    assert reports[0] == reports[1] == reports[2] and len(reports[0]) == 4
+
+
+def test_cli_worker_failure_is_reported(ffr, examples, tmp_path):
+    """More processes than devices: the worker without a device reports through its pipe, the
+    collector prints the error and exits non-zero (no hang, no partial output file)."""
+    n = ffr.lib().ffr_cuda_device_count()
+    flame = tmp_path / "f.json"
+    flame.write_text(examples.example_json("barnsley_fern", size=[64, 64]))
+    out = tmp_path / "x.buf"
+    p = _run_cli(ffr, ["-f", str(flame), "-o", str(out), "-s", "1000000", "-b", "1000", "--seed", "1",
+                       "--gpus", str(n + 1)])
+    assert p.returncode == 1
+    assert "ERROR: worker %d" % n in p.stderr and "device index out of range" in p.stderr
+    assert not out.exists()
