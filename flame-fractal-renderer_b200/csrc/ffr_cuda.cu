@@ -136,6 +136,9 @@ struct DeviceState
     u64 *d_trace = nullptr;        /* only while ffr_cuda_atomic_roofline records a trace */
     void *d_stage = nullptr;       /* staging for add_buffer, kept between calls */
     size_t stage_elems = 0;
+    cudaStream_t copy_stream = nullptr;   /* add_buffer_async: the upload runs on a copy engine, */
+    cudaEvent_t ev_copied = nullptr, ev_added = nullptr;   /* ordered against the add kernel by events */
+    bool stage_busy = false;
     int sm_count = 0;
     int blocks_per_sm = 0;
     bool dirty = false;            /* holds samples not yet reduced into device 0 */
@@ -1197,6 +1200,9 @@ void ffr_cuda_destroy(ffr_ctx *ctx)
         if (ds.jmod.mod) jit::unload(ds.jmod);
         if (ds.jmod_modes.mod) jit::unload(ds.jmod_modes);
         if (ds.d_stage) cudaFree(ds.d_stage);
+        if (ds.copy_stream) cudaStreamDestroy(ds.copy_stream);
+        if (ds.ev_copied) cudaEventDestroy(ds.ev_copied);
+        if (ds.ev_added) cudaEventDestroy(ds.ev_added);
         if (ds.own_stream && ds.stream) cudaStreamDestroy(ds.stream);
     }
     delete ctx;
@@ -1224,19 +1230,16 @@ void *ffr_cuda_device_buffer(ffr_ctx *ctx, int dev_index)
     return ctx->devs[dev_index].buffer;
 }
 
-/* page-locked host memory is mapped into the device's address space (UVA): its device alias, or
-   null for pageable memory */
-static const void *pinned_alias(const void *host)
+/* is this host pointer page-locked (cudaHostAlloc / cudaHostRegister)? */
+static bool is_pinned(const void *host)
 {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a,host) != cudaSuccess)
     {
         cudaGetLastError();
-        return nullptr;
+        return false;
     }
-    if (a.type != cudaMemoryTypeHost || !a.devicePointer)
-        return nullptr;
-    return a.devicePointer;
+    return a.type == cudaMemoryTypeHost;
 }
 
 static int launch_add(ffr_ctx *ctx, DeviceState &ds, void *dst, const void *src, size_t n, size_t first)
@@ -1251,6 +1254,21 @@ static int launch_add(ffr_ctx *ctx, DeviceState &ds, void *dst, const void *src,
     return FFR_OK;
 }
 
+static int ensure_stage(ffr_ctx *ctx, DeviceState &ds, size_t elems)
+{
+    if (ds.stage_elems >= elems)
+        return FFR_OK;
+    CK(cudaStreamSynchronize(ds.stream));
+    if (ds.d_stage)
+        cudaFree(ds.d_stage);
+    ds.d_stage = nullptr;
+    ds.stage_elems = 0;
+    ds.stage_busy = false;
+    CK(cudaMalloc(&ds.d_stage,elems*ctx->elem));
+    ds.stage_elems = elems;
+    return FFR_OK;
+}
+
 int ffr_cuda_add_buffer(ffr_ctx *ctx, const void *host, size_t bytes)
 {
     if (!ctx || !host)
@@ -1262,37 +1280,27 @@ int ffr_cuda_add_buffer(ffr_ctx *ctx, const void *host, size_t bytes)
     }
     DeviceState &ds = ctx->devs[0];
     CK(cudaSetDevice(ds.dev));
+    /* stage in chunks of 128 MiB so that a 1 GiB -i file does not double the footprint; the staging
+       buffer is kept for the next call. Stream order protects its reuse (the copy of chunk k+1
+       starts after the add of chunk k); ONE synchronisation at the end, because the host buffer is
+       only borrowed. */
     const size_t eb = ctx->elem;
     const size_t n_elems = bytes/eb;
-    if (const void *alias = pinned_alias(host))
+    const size_t chunk_elems = ((size_t)1 << 27) / eb;
+    const size_t chunk = std::min(n_elems,chunk_elems - (chunk_elems % ctx->cellsz));
+    int rc = ensure_stage(ctx,ds,chunk);
+    if (rc != FFR_OK)
+        return rc;
+    if (ds.stage_busy)
     {
-        /* page-locked memory: the add kernel reads it in place over PCIe */
-        int rc = launch_add(ctx,ds,ds.buffer,alias,n_elems,0);
-        if (rc != FFR_OK)
-            return rc;
-        CK(cudaStreamSynchronize(ds.stream));
-        return FFR_OK;
-    }
-    /* pageable memory: stage in chunks so that a 1 GiB -i file does not double the footprint; the
-       staging buffer is kept for the next call. Stream order protects its reuse (the copy of
-       chunk k+1 starts after the add of chunk k); one synchronisation at the end, because the
-       host buffer is only borrowed. */
-    const size_t chunk_elems = ((size_t)1 << 27) / eb; /* 128 MiB */
-    size_t chunk = std::min(n_elems,chunk_elems - (chunk_elems % ctx->cellsz));
-    if (ds.stage_elems < chunk)
-    {
-        if (ds.d_stage)
-            cudaFree(ds.d_stage);
-        ds.d_stage = nullptr;
-        ds.stage_elems = 0;
-        CK(cudaMalloc(&ds.d_stage,chunk*eb));
-        ds.stage_elems = chunk;
+        CK(cudaStreamWaitEvent(ds.stream,ds.ev_added,0));
+        ds.stage_busy = false;
     }
     for (size_t off = 0; off < n_elems; off += chunk)
     {
-        size_t n = std::min(chunk,n_elems - off);
+        const size_t n = std::min(chunk,n_elems - off);
         CK(cudaMemcpyAsync(ds.d_stage,(const char*)host + off*eb,n*eb,cudaMemcpyHostToDevice,ds.stream));
-        int rc = launch_add(ctx,ds,(char*)ds.buffer + off*eb,ds.d_stage,n,off);
+        rc = launch_add(ctx,ds,(char*)ds.buffer + off*eb,ds.d_stage,n,off);
         if (rc != FFR_OK)
             return rc;
     }
@@ -1323,13 +1331,35 @@ int ffr_cuda_add_buffer_async(ffr_ctx *ctx, const void *pinned_host, size_t byte
     }
     DeviceState &ds = ctx->devs[0];
     CK(cudaSetDevice(ds.dev));
-    const void *alias = pinned_alias(pinned_host);
-    if (!alias)
+    if (!is_pinned(pinned_host))
     {
         ctx->err = "add_buffer_async: the host buffer must be page-locked";
         return FFR_E_INVALID;
     }
-    return launch_add(ctx,ds,ds.buffer,alias,bytes/ctx->elem,0);
+    /* the whole buffer is uploaded by a copy engine on a stream of its own -- it overlaps whatever
+       kernels run meanwhile, a render of another context in particular -- into a full-size staging
+       buffer (this interface trades memory for overlap); the add kernel then runs on the
+       context's stream, ordered after the copy by an event, and the next upload after this add */
+    int rc = ensure_stage(ctx,ds,bytes/ctx->elem);
+    if (rc != FFR_OK)
+        return rc;
+    if (!ds.copy_stream)
+    {
+        CK(cudaStreamCreateWithFlags(&ds.copy_stream,cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ds.ev_copied,cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ds.ev_added,cudaEventDisableTiming));
+    }
+    if (ds.stage_busy)
+        CK(cudaStreamWaitEvent(ds.copy_stream,ds.ev_added,0));
+    CK(cudaMemcpyAsync(ds.d_stage,pinned_host,bytes,cudaMemcpyHostToDevice,ds.copy_stream));
+    CK(cudaEventRecord(ds.ev_copied,ds.copy_stream));
+    CK(cudaStreamWaitEvent(ds.stream,ds.ev_copied,0));
+    rc = launch_add(ctx,ds,ds.buffer,ds.d_stage,bytes/ctx->elem,0);
+    if (rc != FFR_OK)
+        return rc;
+    CK(cudaEventRecord(ds.ev_added,ds.stream));
+    ds.stage_busy = true;
+    return FFR_OK;
 }
 
 int ffr_cuda_read_buffer_async(ffr_ctx *ctx, void *pinned_host, size_t bytes)
@@ -1345,7 +1375,7 @@ int ffr_cuda_read_buffer_async(ffr_ctx *ctx, void *pinned_host, size_t bytes)
     }
     DeviceState &ds = ctx->devs[0];
     CK(cudaSetDevice(ds.dev));
-    if (!pinned_alias(pinned_host))
+    if (!is_pinned(pinned_host))
     {
         ctx->err = "read_buffer_async: the host buffer must be page-locked";
         return FFR_E_INVALID;

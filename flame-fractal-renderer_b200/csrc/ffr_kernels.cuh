@@ -765,8 +765,7 @@ __global__ void add_buffer_kernel(typename Real<T>::word *__restrict__ dst,
 {
     typedef typename Real<T>::word W;
     const u64 stride = (u64)gridDim.x*blockDim.x;
-    /* four independent loads in flight per thread: src may be page-locked host memory read over
-       PCIe, where latency is microseconds */
+    /* four independent loads in flight per thread (src may be a peer's memory over NVLink) */
     for (u64 i0 = (u64)blockIdx.x*blockDim.x + threadIdx.x; i0 < n_elems; i0 += 4*stride)
     {
         W s[4];

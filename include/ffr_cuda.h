@@ -323,7 +323,8 @@ int ffr_cuda_render_chains_async(ffr_ctx *ctx, uint64_t chain_first, uint64_t ch
    overlaps one context's PCIe legs with the other's render (bench.py's e2e loop does). The host
    buffers must be PAGE-LOCKED (cudaHostAlloc / cudaHostRegister / torch pin_memory) and stay
    valid and untouched until ffr_cuda_sync returns; pageable memory is refused (FFR_E_INVALID).
-   The add reads the pinned buffer directly over PCIe (no staging copy). */
+   The upload of the add runs on a copy engine (a stream of its own, ordered by events) into a
+   full-size staging buffer kept by the context. */
 int ffr_cuda_clear_buffer_async(ffr_ctx *ctx);
 int ffr_cuda_add_buffer_async(ffr_ctx *ctx, const void *pinned_host, size_t bytes);
 int ffr_cuda_read_buffer_async(ffr_ctx *ctx, void *pinned_host, size_t bytes);

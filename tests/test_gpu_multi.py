@@ -201,7 +201,7 @@ def test_atomic_roofline_patterns(ffr, examples):
 def test_streaming_interface_equals_blocking_calls(ffr, po, examples):
     """ffr_cuda_{clear,add_buffer,read_buffer}_async + render_chains_async on page-locked
     buffers give the buffer the blocking calls give; pageable host memory is refused; the
-    blocking add takes the zero-copy path for pinned memory and the staged path otherwise."""
+    blocking add gives the same result from pinned and from pageable host memory."""
     import torch
     fl = ffr.Flame(examples.example_json("tkoz_test3", size=[320, 200]))   # mixed u64 / f64 cells
     _, _, cells, cs = fl.layout()
@@ -224,7 +224,7 @@ def test_streaming_interface_equals_blocking_calls(ffr, po, examples):
         r.read_buffer_async(np.zeros(cells * cs, dtype=np.uint64))
     r.close()
     want = []
-    for src in (in_np, prev):    # pinned (zero-copy add) and pageable (staged add)
+    for src in (in_np, prev):    # pinned and pageable host memory
         b = ffr.BufferRenderer(fl)
         b.add_buffer(src)
         assert b.render_chains(0, 300, 700, base_seed=5)
