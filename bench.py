@@ -18,8 +18,8 @@ value     device-timed (CUDA events on the launching stream) throughput of K ste
 e2e       the same metric through the reference-facing C ABI with HOST buffers: every step
           uploads a pinned host buffer (the -i resume path), renders and reads the whole buffer
           back to pinned host memory -- H2D and D2H inside the timed region. At N = 1 the steps go
-          through the library's streaming interface (ffr_cuda_*_async) on two contexts used
-          alternately, so one step's read-back overlaps the next step's upload and render; at
+          through the library's streaming interface (ffr_cuda_*_async) on three contexts used in
+          turn, so a step's upload, render and read-back overlap its neighbours' other legs; at
           N > 1 through the blocking calls around the NCCL reduce.
 roofline  HBM: algorithmic bytes (one RMW of one cell per PLOTTED sample = 2*(1+r)*8 B) per
           launch / average launch duration, against MEASURED_PEAKS.json hbm_gbs.
@@ -405,47 +405,49 @@ class Bench:
                 if rank == 0:
                     e2e_rend.read_buffer(out_np)
         else:
-            # two contexts on two streams, used alternately: step k+1's upload and render overlap
-            # step k's read-back (the library's streaming interface; every step still uploads its
-            # input from pinned host memory and reads its whole result back)
+            # three contexts on three streams, used in turn: a step's upload (copy engine), render
+            # (SMs) and read-back (copy engine) overlap the neighbouring steps' other legs (the
+            # library's streaming interface; every step still uploads its input from pinned host
+            # memory and reads its whole result back)
             e2e_rend = ffr.BufferRenderer(flame, devices=[self.local_rank], jit=self.jit)
-            e2e_rend2 = ffr.BufferRenderer(flame, devices=[self.local_rank], jit=self.jit)
-            host_out2 = torch.zeros(n_elems, dtype=torch.int64).pin_memory()
-            out2_np = host_out2.numpy().view(np.uint64)
-            pipe = [(e2e_rend, out_np), (e2e_rend2, out2_np)]
+            extra = [ffr.BufferRenderer(flame, devices=[self.local_rank], jit=self.jit) for _ in range(2)]
+            extra_host = [torch.zeros(n_elems, dtype=torch.int64).pin_memory() for _ in range(2)]
+            pipe = [(e2e_rend, out_np)] + [(r, h.numpy().view(np.uint64)) for r, h in zip(extra, extra_host)]
 
             def e2e_step(k):
-                r, out = pipe[k % 2]
-                r.sync()                      # this context's previous step (two steps ago)
+                r, out = pipe[k % 3]
+                r.sync()                      # this context's previous step (three steps ago)
                 r.clear_async()
                 r.add_buffer_async(in_np)
                 first = (k + 500_000) * chains_per_step
                 r.render_chains_async(first, chains_per_step, L, base_seed=1)
                 r.read_buffer_async(out)
 
-        e2e_steps = max(4, min(steps, 20))
-        e2e_step(-2)
-        e2e_step(-1)
+        e2e_steps = max(6, min(steps, 20))
+        for k in (-3, -2, -1):
+            e2e_step(k)
         if world == 1:
-            e2e_rend.sync()
-            e2e_rend2.sync()
+            for r, _ in pipe:
+                r.sync()
         self.barrier()
         t0 = time.perf_counter()
         for k in range(e2e_steps):
             e2e_step(k)
         if world == 1:
-            e2e_rend.sync()
-            e2e_rend2.sync()
+            for r, _ in pipe:
+                r.sync()
         self.barrier()
         e2e_s = self.max_over_ranks(time.perf_counter() - t0)
         e2e_value = samples_per_step * e2e_steps * world / e2e_s
         if world == 1:
             # the result of the last step really arrived: every sample of a step is iterated once
-            st_a, st_b = e2e_rend.fetch_stats(), e2e_rend2.fetch_stats()
-            assert st_a["s_iter"] + st_b["s_iter"] == samples_per_step * (e2e_steps + 2)
-            assert int(out_np.sum() + out2_np.sum()) > 0 if cell == 1 else True
-            e2e_rend2.close()
-            del host_out2, out2_np
+            done = sum(r.fetch_stats()["s_iter"] for r, _ in pipe)
+            assert done == samples_per_step * (e2e_steps + 3), (done, samples_per_step, e2e_steps)
+            if cell == 1:
+                assert all(int(o[::4097].sum()) > 0 for _, o in pipe)
+            for r in extra:
+                r.close()
+            del extra_host, pipe
         e2e_rend.close()
         del buf, ebuf, host_in, host_out, in_np, out_np
         torch.cuda.empty_cache()

@@ -5,6 +5,7 @@ point that computes needs an sm_100 device and fails loudly without one.
 */
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -1075,6 +1076,19 @@ ffr_ctx *ffr_cuda_create(const ffr_flame_desc *desc, const int *devices, int nde
 ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int ndev,
         const ffr_options *opt, char *err, size_t errlen)
 {
+    /* FFR_TIMING=1: where the time to a ready context goes (stderr) */
+    const bool timing = getenv("FFR_TIMING") && *getenv("FFR_TIMING") == '1';
+    timespec t_begin;
+    clock_gettime(CLOCK_MONOTONIC,&t_begin);
+    auto lap = [&](const char *what)
+    {
+        if (!timing)
+            return;
+        timespec t;
+        clock_gettime(CLOCK_MONOTONIC,&t);
+        fprintf(stderr,"timing[%d]: create: %s at %.3f s\n",(int)getpid(),what,
+            (double)(t.tv_sec - t_begin.tv_sec) + 1e-9*(double)(t.tv_nsec - t_begin.tv_nsec));
+    };
     ffr_ctx *ctx = new ffr_ctx;
     std::string msg;
     auto fail = [&](const std::string& m) -> ffr_ctx*
@@ -1096,6 +1110,7 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
     if ((ctx->opt.external_buffer || ctx->opt.stream) && ndev != 1)
         return fail("ffr_cuda_create(): external buffer / stream need a single device context");
     int avail = ffr_cuda_device_count();
+    lap("driver initialised (cudaGetDeviceCount)");
     if (avail < 1)
         return fail("ffr_cuda_create(): no CUDA device available; libffr_cuda has no CPU fallback");
     ctx->scatter_mode = ctx->opt.scatter_mode;
@@ -1140,6 +1155,7 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
         for (std::thread &t : warm)
             t.join();
         cudaGetLastError();
+        lap("primary contexts created");
     }
     for (int i = 0; i < ndev; ++i)
     {
@@ -1149,6 +1165,7 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
         int rc = setup_device(ctx,ctx->devs[i],dev,ctx->opt);
         if (rc != FFR_OK)
             return fail(ctx->err);
+        lap("device set up (context, module, buffer)");
     }
     /* K1c/K1d (run-time compiled). opt.jit: 0 auto = compiled lazily by the first render call of
        >= FFR_JIT_MIN_SAMPLES samples, for flames with variations other than linear; 1 never;
@@ -1170,6 +1187,7 @@ ffr_ctx *ffr_cuda_create_ex(const ffr_flame_desc *desc, const int *devices, int 
             return fail("ffr_cuda_create(): the flame-specialised kernel supports <= 8 xforms and <= 4 colour dimensions");
         if (jit_activate(ctx) != FFR_OK)
             return fail("ffr_cuda_create(): run-time compilation failed: " + (ctx->jit_err.empty() ? ctx->err : ctx->jit_err));
+        lap("flame-specialised kernel compiled/loaded");
     }
     else if (ctx->jit_mode == 2 && ctx->jit_eligible)
         jit_activate(ctx);   /* FFR_JIT=1: best effort, the interpreter kernels remain */

@@ -152,11 +152,28 @@ static void chain_range(uint64_t chains, int nproc, int rank, uint64_t *first, u
     static WorkerMsg msg;
     memset(&msg,0,sizeof(msg));
     ffr_options opt = opt0;
-    ffr_ctx *ctx = ffr_cuda_create_ex(desc,&rank,1,&opt,msg.err,sizeof(msg.err));
+    /* FFR_WORKER_MASK=1: the worker sees only its own GPU (CUDA_VISIBLE_DEVICES, entry `rank` of an
+       inherited list), so that its driver initialisation does not touch the other devices */
+    int dev = rank;
+    if (getenv("FFR_WORKER_MASK") && *getenv("FFR_WORKER_MASK") == '1')
+    {
+        std::string mine = std::to_string(rank);
+        if (const char *vis = getenv("CUDA_VISIBLE_DEVICES"))
+        {
+            std::stringstream ss(vis);
+            std::string item;
+            for (int k = 0; std::getline(ss,item,','); ++k)
+                if (k == rank)
+                    mine = item;
+        }
+        setenv("CUDA_VISIBLE_DEVICES",mine.c_str(),1);
+        dev = 0;
+    }
+    ffr_ctx *ctx = ffr_cuda_create_ex(desc,&dev,1,&opt,msg.err,sizeof(msg.err));
     if (!ctx && opt.jit == 2)
     {
         opt.jit = 1;
-        ctx = ffr_cuda_create_ex(desc,&rank,1,&opt,msg.err,sizeof(msg.err));
+        ctx = ffr_cuda_create_ex(desc,&dev,1,&opt,msg.err,sizeof(msg.err));
     }
     if (!ctx)
         msg.rc = FFR_E_CUDA;
@@ -362,9 +379,8 @@ int main(int argc, char **argv)
     const uint64_t last_chain = arg_samples - (total_chains ? (total_chains - 1)*arg_batch_size : 0);
     const uint64_t last_len = (last_chain == arg_batch_size) ? 0 : last_chain;
 
-    /* --gpus N: one process per GPU. Nothing below this point has touched CUDA yet, so forking is
-       safe; the run-time compiled kernel is built ONCE, before the fork (NVRTC needs no device), and
-       the workers inherit it through the library's in-process cache. */
+    /* --gpus N: one process per GPU. Nothing up to this point has touched CUDA or NVRTC, so forking
+       is safe. */
     const bool single = getenv("FFR_SINGLE_PROCESS") && *getenv("FFR_SINGLE_PROCESS") == '1';
     const int nproc = (arg_gpus > 1 && !single && arg_samples > 0) ? arg_gpus : 1;
     std::vector<pid_t> pids;
@@ -378,17 +394,10 @@ int main(int argc, char **argv)
         }
         if (opt.jit == 0 && arg_samples >= 50000000000ull)
             opt.jit = 2;        /* the auto threshold applies to the job, not to one process's share */
-        if (opt.jit == 2)
-        {
-            char jerr[512];
-            if (ffr_cuda_jit_compile(desc,nullptr,0,nullptr,jerr,sizeof(jerr)) != FFR_OK)
-            {
-                if (arg_jit == 2)
-                    std::cerr << "note: " << jerr << "; using the ahead-of-time kernels" << std::endl;
-                opt.jit = 1;
-            }
-        }
-        phase("kernel compiled");
+        /* No NVRTC here: a process that has compiled cannot hand a usable CUDA state to its forked
+           children (measured: the workers then find no device). Every process compiles for itself,
+           all at once -- the wall-clock cost of one compile -- unless the kernel is in the disk
+           cache already. */
         signal(SIGPIPE,SIG_IGN);
         for (int r = 1; r < nproc; ++r)
         {
