@@ -310,6 +310,10 @@ class Bench:
             launch_step(1_000_000 + w)
         self.barrier()
         step_s = (time.perf_counter() - t_w) / warmup
+        # the exchange step once, untimed: NCCL sets up its peer connections on first use (seconds
+        # at N = 8), a one-off like the creation of the context
+        sharding.reduce_buffer(buf, cells, cell, dst=0, renderer=rend)
+        self.barrier()
         if min_seconds > 0:
             steps = max(steps, int(min_seconds / max(step_s, 1e-4)) + 1)
         buf.zero_()

@@ -17,13 +17,15 @@ options:
 -b,--batch-size   samples per chain (work unit); 0 = calculate a reasonable size
 -z,--bad-values   number of bad values allowed before terminating render
    --seed         base seed of the per-chain ISAAC streams (default: clock)
-   --gpus         number of GPUs to shard the chains over (default 1). N > 1 runs one PROCESS per
-                  GPU (fork before any CUDA call): creating N CUDA contexts inside one process is
-                  serialised by the driver (8 GPUs: 7.5 s before the first kernel), N processes
-                  create theirs in parallel. The workers render their chain ranges into private
-                  buffers; the first process adds them to its own over NVLink peer memory (CUDA
-                  IPC) and writes the output. FFR_SINGLE_PROCESS=1 keeps everything in one process
-                  (the library's multi-device context).
+   --gpus         number of GPUs to shard the chains over (default 1): one process, the library's
+                  multi-device context (private buffers, peer reduce-scatter at the end).
+                  FFR_MULTI_PROCESS=1 runs one PROCESS per GPU instead (fork before any CUDA call;
+                  the workers render their chain ranges into private buffers, the first process
+                  adds them to its own over NVLink peer memory through CUDA IPC and writes the
+                  output). Measured on the 8 x B200 box: the driver initialises ~0.7 s per visible
+                  GPU and process, serialised system-wide, so eight processes (10.4-11.5 s to a
+                  ready context) lose to one (7.1 s, of which 5.9 s are cuInit itself); on two GPUs
+                  the two forms are level (2.2 s vs 2.7 s). Hence the default.
    --float        the reference's float/uint32_t build (types.hpp:24-41) instead of the shipped
                   double/uint64_t one: 4-byte buffer elements, ISAAC-32
 */
@@ -381,8 +383,8 @@ int main(int argc, char **argv)
 
     /* --gpus N: one process per GPU. Nothing up to this point has touched CUDA or NVRTC, so forking
        is safe. */
-    const bool single = getenv("FFR_SINGLE_PROCESS") && *getenv("FFR_SINGLE_PROCESS") == '1';
-    const int nproc = (arg_gpus > 1 && !single && arg_samples > 0) ? arg_gpus : 1;
+    const bool multi = getenv("FFR_MULTI_PROCESS") && *getenv("FFR_MULTI_PROCESS") == '1';
+    const int nproc = (arg_gpus > 1 && multi && arg_samples > 0) ? arg_gpus : 1;
     std::vector<pid_t> pids;
     std::vector<int> up_fds, down_fds;
     if (nproc > 1)
@@ -648,5 +650,13 @@ int main(int argc, char **argv)
     ffr_cuda_destroy(ctx);
     ffr_flame_free(flame);
     phase("context destroyed");
+    /* everything is written and closed: leave without the CUDA runtime's exit handlers, which take
+       ~0.35 s per device to unwind the primary contexts one after the other (8 devices: 2.8 s of an
+       11.4 s run); the operating system reclaims the devices either way. FFR_CLEAN_EXIT=1 returns
+       normally. */
+    std::cerr.flush();
+    std::cout.flush();
+    if (!(getenv("FFR_CLEAN_EXIT") && *getenv("FFR_CLEAN_EXIT") == '1'))
+        _exit(0);
     return 0;
 }

@@ -253,9 +253,10 @@ def _run_cli(ffr, args, env=None):
                                             ("tkoz_test3", [192, 108], "--jit"),
                                             ("csci6360_project", [192, 108], "--jit")])
 def test_cli_one_process_per_gpu_equals_one_gpu(ffr, examples, tmp_path, name, size, flag):
-    """ffr-buf.out --gpus 2: two processes (fork before any CUDA call), the worker's buffer added
-    to the collector's over CUDA IPC peer memory. Counts byte-identical to the 1-GPU file, the
-    same stderr report (s_iter, s_plot, xform selection); also the single-process form."""
+    """ffr-buf.out --gpus 2, both forms: one process with a two-device context (default), and
+    FFR_MULTI_PROCESS=1: two processes (fork before any CUDA call), the worker's buffer added to
+    the collector's over CUDA IPC peer memory. Counts byte-identical to the 1-GPU file, the same
+    stderr report (s_iter, s_plot, xform selection)."""
     if ffr.lib().ffr_cuda_device_count() < 2:
         pytest.skip("needs 2 GPUs")
     flame = tmp_path / "f.json"
@@ -265,7 +266,7 @@ def test_cli_one_process_per_gpu_equals_one_gpu(ffr, examples, tmp_path, name, s
     common = ["-f", str(flame), "-s", "3000000", "-b", "1000", "--seed", "11", flag]
     outs, reports = [], []
     for tag, extra, env in (("one", [], None), ("two", ["--gpus", "2"], None),
-                            ("two_sp", ["--gpus", "2"], {"FFR_SINGLE_PROCESS": "1"})):
+                            ("two_mp", ["--gpus", "2"], {"FFR_MULTI_PROCESS": "1"})):
         out = tmp_path / (tag + ".buf")
         p = _run_cli(ffr, common + ["-o", str(out)] + extra, env)
         assert p.returncode == 0, p.stderr
@@ -290,7 +291,11 @@ def test_cli_worker_failure_is_reported(ffr, examples, tmp_path):
     flame.write_text(examples.example_json("barnsley_fern", size=[64, 64]))
     out = tmp_path / "x.buf"
     p = _run_cli(ffr, ["-f", str(flame), "-o", str(out), "-s", "1000000", "-b", "1000", "--seed", "1",
-                       "--gpus", str(n + 1)])
+                       "--gpus", str(n + 1)], {"FFR_MULTI_PROCESS": "1"})
     assert p.returncode == 1
     assert "ERROR: worker %d" % n in p.stderr and "device index out of range" in p.stderr
     assert not out.exists()
+    # the default form (one process) reports the same condition itself
+    p = _run_cli(ffr, ["-f", str(flame), "-o", str(out), "-s", "1000000", "-b", "1000", "--seed", "1",
+                       "--gpus", str(n + 1)])
+    assert p.returncode == 1 and "device index out of range" in p.stderr and not out.exists()
