@@ -160,6 +160,7 @@ struct ffr_ctx
     uint32_t dims = 0, r = 0, cellsz = 1;
     uint32_t elem = 8;             /* sizeof(num_t) == sizeof(hist_t): 8 double/u64, 4 float/u32 */
     uint32_t size0 = 1, size1 = 1;
+    u64 sizes[3] = {1,1,1};
     u64 cells = 0;
     size_t bytes = 0;
     uint32_t num_xforms = 0, num_ids = 0;
@@ -487,6 +488,8 @@ bool pack_blob(ffr_ctx *ctx, const ffr_flame_desc *d, std::string &err)
     if (!vars.empty())
         memcpy(ctx->blob.data()+hdr.var_off,vars.data(),vars.size()*sizeof(DevVarT<T>));
     ctx->dims = d->dims;
+    for (uint32_t i = 0; i < 3; ++i)
+        ctx->sizes[i] = i < d->dims ? d->size[i] : 1;
     ctx->size0 = (uint32_t)d->size[0];
     ctx->size1 = d->dims > 1 ? (uint32_t)d->size[1] : 1;
     ctx->r = d->color_dims;
@@ -645,6 +648,14 @@ bool jit_prepare(ffr_ctx *ctx, bool cache_only = false)
                 const u64 tile_bytes = (u64)env_int("FFR_DIR_TILE_MB",192) << 20;
                 cfg.dir_cap = (unsigned)std::min<u64>(tile_bytes/((u64)ctx->elem << FFR_DIR_ROW_SHIFT),
                                                       ctx->cells >> FFR_DIR_ROW_SHIFT);
+                /* rows as BLOCKS of cells where every size is a multiple of the block's extent
+                   (FFR_DIR_BLOCKED=0: 512 consecutive cells, the round-1 layout) */
+                static const unsigned shape[4][3] = {{0,0,0},{9,0,0},{5,4,0},{3,3,3}};
+                bool ok = env_int("FFR_DIR_BLOCKED",1) != 0 && ctx->dims >= 1 && ctx->dims <= 3;
+                for (uint32_t d = 0; ok && d < ctx->dims; ++d)
+                    ok = ctx->sizes[d] % (1u << shape[ctx->dims][d]) == 0 && ctx->sizes[d] < (1ULL << 31);
+                for (uint32_t d = 0; d < 3; ++d)
+                    cfg.dir_blk[d] = ok ? shape[ctx->dims][d] : 0u;
             }
         }
         std::string why;
@@ -665,7 +676,11 @@ bool jit_prepare(ffr_ctx *ctx, bool cache_only = false)
             ctx->jit_compile_s += secs;
             ctx->jit_note += std::string("K1e pure-affine kernel, ") +
                 (cfg.acc_mul ? (cfg.acc_gran ? "sector-scrambled accumulation tile, " : "cell-scrambled accumulation tile, ") : "") +
-                (cfg.dir_cap ? "compact tile of " + std::to_string(cfg.dir_cap) + " rows, " : std::string()) +
+                (cfg.dir_cap ? "compact tile of " + std::to_string(cfg.dir_cap) + " rows" +
+                    ((cfg.dir_blk[0] | cfg.dir_blk[1] | cfg.dir_blk[2]) ? " (blocks of " + std::to_string(1u << cfg.dir_blk[0]) +
+                        (ctx->dims > 1 ? "x" + std::to_string(1u << cfg.dir_blk[1]) : std::string()) +
+                        (ctx->dims > 2 ? "x" + std::to_string(1u << cfg.dir_blk[2]) : std::string()) + " cells)" : std::string()) + ", "
+                  : std::string()) +
                 std::to_string(cfg.npair) + " table rows, tpb " +
                 std::to_string(cfg.tpb) + ": " + std::to_string(spills) + " spill bytes; ";
             return true;
@@ -864,10 +879,19 @@ int fold_tiles(ffr_ctx *ctx, DeviceState &ds)
         /* K2c: the compact tile's rows into the buffer */
         const u64 rows = ctx->cells >> FFR_DIR_ROW_SHIFT;
         const unsigned fgrid = (unsigned)std::min<u64>((rows + 7)/8,(u64)ds.sm_count*16);
+        DirGeom g;
+        u64 mult = 1;
+        for (uint32_t d = 0; d < 3; ++d)
+        {
+            g.blk[d] = ctx->jit_cfg.dir_blk[d];
+            g.rows[d] = (uint32_t)std::max<u64>(1,ctx->sizes[d] >> g.blk[d]);
+            g.mult[d] = mult;
+            mult *= ctx->sizes[d];
+        }
         if (ctx->elem == 8)
-            fold_dir_kernel<u64><<<fgrid,256,0,ds.stream>>>((u64*)ds.d_acc,(u64*)ds.buffer,ds.d_dir,rows);
+            fold_dir_kernel<u64><<<fgrid,256,0,ds.stream>>>((u64*)ds.d_acc,(u64*)ds.buffer,ds.d_dir,rows,g);
         else
-            fold_dir_kernel<unsigned int><<<fgrid,256,0,ds.stream>>>((unsigned int*)ds.d_acc,(unsigned int*)ds.buffer,ds.d_dir,rows);
+            fold_dir_kernel<unsigned int><<<fgrid,256,0,ds.stream>>>((unsigned int*)ds.d_acc,(unsigned int*)ds.buffer,ds.d_dir,rows,g);
     }
     else
     {

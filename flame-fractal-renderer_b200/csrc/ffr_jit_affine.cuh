@@ -33,7 +33,8 @@ int -> fp conversion of the selection draw, unconditional min/max selects. Here:
    attractor's cell addresses are strongly patterned and load the L2 slices unevenly;
  * for buffers beyond the reach of the address translation (> 256 MiB) the launch scatters into
    a compact tile of 4 KiB rows allocated on first touch through a row directory (JDIR_CAP,
-   fold_dir_kernel): a sparse attractor's hot rows then span tens of MiB instead of 1 GiB.
+   fold_dir_kernel): a sparse attractor's hot rows then span tens of MiB instead of 1 GiB. A row
+   is a BLOCK of 512 cells (8x8x8 in 3-d, 32x16 in 2-d; JDIR_BLOCKED) where the sizes allow it.
 
 Everything else is the reference's arithmetic in the reference's order (-fmad=false), so the
 histogram counts and statistics equal K1's bit for bit (tests/test_gpu_jit.py).
@@ -336,7 +337,13 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
                     }
                     if (in)
                     {
+#ifdef JDIR_BLOCKED
+                        unsigned brow, boff;
+                        JIDX bi;
+                        jaf_dir_split(p,brow,boff,bi); /* :202-209 + the cell's block row */
+#else
                         const JIDX bi = jaf_index(p); /* :202-209 */
+#endif
                         W *cell = buffer + bi;
 #if defined(JACC_MUL) || defined(JDIR_CAP)
                         /* the diagnostics scatter into the buffer itself; the trace records the
@@ -355,15 +362,20 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
                            yet", which sends the lane to the coherent slow path. */
                         if (tiled)
                         {
+#ifdef JDIR_BLOCKED
+                            /* rows are BLOCKS of cells (8x8x8, 32x16): an attractor of fractal dimension
+                               d < D touches far fewer blocks than runs of 512 consecutive cells, so the
+                               hot part of the directory stays in L1 */
+                            const unsigned row = brow, off = boff;
+#else
                             const unsigned row = (unsigned)(bi >> FFR_DIR_ROW_SHIFT);
+                            const unsigned off = (unsigned)bi & ((1u << FFR_DIR_ROW_SHIFT) - 1u);
+#endif
                             unsigned slot = __ldca(&prm.dir[row]);
                             if (slot >= FFR_DIR_DIRECT)
                                 slot = jaf_dir_slow(prm.dir,prm.dir_next,row);
                             if (slot < FFR_DIR_DIRECT)
-                            {
-                                unsigned off = (unsigned)bi & ((1u << FFR_DIR_ROW_SHIFT) - 1u);
                                 cell = acc + (((u64)slot << FFR_DIR_ROW_SHIFT) | off);
-                            }
                         }
 #endif
                         if (!MODES)

@@ -49,6 +49,8 @@ struct Config
     unsigned acc_mul = 0;   /* K1e: scramble multiplier of the accumulation tile (0: scatter into the buffer) */
     unsigned acc_gran = 0;  /* K1e: log2 of the cells that stay together in the tile */
     unsigned dir_cap = 0;   /* K1e: rows of the compact tile (0: none); excludes acc_mul */
+    unsigned dir_blk[3] = {0,0,0};   /* K1e compact tile: log2 of a row's extent along each axis (sum 9: a row is
+                                        a BLOCK of 512 cells, e.g. 8x8x8); all zero: 512 consecutive cells */
 };
 
 struct Api
@@ -680,6 +682,8 @@ std::string generate_affine(const std::vector<unsigned char> &blobv, const u64 *
         if (cfg.dir_cap)
             h << "#define JDIR_CAP " << cfg.dir_cap << "u\n#define JACC_ELEMS "
               << ((unsigned long long)cfg.dir_cap << FFR_DIR_ROW_SHIFT) << "ULL\n";
+        if (cfg.dir_cap && (cfg.dir_blk[0] | cfg.dir_blk[1] | cfg.dir_blk[2]))
+            h << "#define JDIR_BLOCKED 1\n";
         h << "\n";
         o << "/* XForm::applyIteration for every xform of the flame; tb = coefficient table + xform index */\n";
         if (p_nz)
@@ -733,6 +737,29 @@ std::string generate_affine(const std::vector<unsigned char> &blobv, const u64 *
             o << "    bi += (JIDX)" << cvt << "((pf[" << i << "] - " << pool.ref(fl->lo[i]) << ") * " << pool.ref(fl->mult_d[i]) << ") * (JIDX)"
               << fl->mult_i[i] << "ULL;\n";
         o << "    return bi;\n}\n\n";
+        if (cfg.dir_cap && (cfg.dir_blk[0] | cfg.dir_blk[1] | cfg.dir_blk[2]))
+        {
+            /* compact tile with BLOCK rows: the row a cell belongs to and its place inside, from the
+               per-axis cell coordinates; bi (the reference's linear index, :202-209) is only used
+               when the row has no slot in the tile */
+            o << "__device__ __forceinline__ void jaf_dir_split(const JT *pf, unsigned &row, unsigned &off, JIDX &bi)\n{\n";
+            u64 row_mult = 1;
+            unsigned off_shift = 0;
+            std::string row_e, off_e, bi_e;
+            for (int i = 0; i < D; ++i)
+            {
+                o << "    const unsigned c" << i << " = " << (idx32 ? cvt : (sizeof(T) == 8 ? "(unsigned)__double2ull_rz" : "(unsigned)__float2ull_rz"))
+                  << "((pf[" << i << "] - " << pool.ref(fl->lo[i]) << ") * " << pool.ref(fl->mult_d[i]) << ");\n";
+                const u64 size_i = (i + 1 < D) ? fl->mult_i[i + 1]/fl->mult_i[i] : fl->cells/fl->mult_i[i];
+                const unsigned b = cfg.dir_blk[i];
+                row_e += (i ? " + " : "") + std::string("(c") + std::to_string(i) + " >> " + std::to_string(b) + ")*" + std::to_string(row_mult) + "u";
+                off_e += (i ? " | " : "") + std::string("((c") + std::to_string(i) + " & " + std::to_string((1u << b) - 1u) + "u) << " + std::to_string(off_shift) + ")";
+                bi_e += (i ? " + " : "") + std::string("(JIDX)c") + std::to_string(i) + "*(JIDX)" + std::to_string(fl->mult_i[i]) + "ULL";
+                row_mult *= size_i >> b;
+                off_shift += b;
+            }
+            o << "    row = " << row_e << ";\n    off = " << off_e << ";\n    bi = " << bi_e << ";\n}\n\n";
+        }
         o << "__device__ __forceinline__ u64 jit_json_id(unsigned k)\n{\n    switch (k)\n    {\n";
         for (int k = 0; k < NX; ++k)
             o << "    case " << k << ": return " << xfs[k].json_id << "ULL;\n";

@@ -730,26 +730,50 @@ __global__ void fold_acc_kernel(W *__restrict__ acc, W *__restrict__ buffer, u64
    into rows of 512 cells allocated on first touch in a tile of <= 192 MiB; dir[row] is the
    row's slot. One warp per row; the tile is left all zero, the directory stays (rows keep their
    slots for the context's lifetime). */
+/* geometry of BLOCK rows: blk[d] = log2 of a row's extent along axis d (sum FFR_DIR_ROW_SHIFT),
+   rows[d] = blocks along axis d, mult[d] = the reference's index multiplier of axis d. All blk
+   zero: a row is 512 consecutive cells. */
+struct DirGeom
+{
+    uint32_t blk[3], rows[3];
+    u64 mult[3];
+};
+
 template <typename W>
 __global__ void fold_dir_kernel(W *__restrict__ tile, W *__restrict__ buffer, const unsigned int *__restrict__ dir,
-        u64 rows)
+        u64 rows, const DirGeom g)
 {
     const u64 warps = ((u64)gridDim.x*blockDim.x) >> 5;
     const unsigned lane = threadIdx.x & 31u;
+    const bool blocked = (g.blk[0] | g.blk[1] | g.blk[2]) != 0;
     for (u64 row = ((u64)blockIdx.x*blockDim.x + threadIdx.x) >> 5; row < rows; row += warps)
     {
         const unsigned int slot = dir[row];
         if (slot >= FFR_DIR_DIRECT)
             continue;
         W *t = tile + ((u64)slot << FFR_DIR_ROW_SHIFT);
-        W *b = buffer + (row << FFR_DIR_ROW_SHIFT);
+        u64 base = row << FFR_DIR_ROW_SHIFT;
+        if (blocked)
+        {
+            const u64 r0 = row % g.rows[0], r12 = row / g.rows[0];
+            const u64 r1 = r12 % g.rows[1], r2 = r12 / g.rows[1];
+            base = (r0 << g.blk[0])*g.mult[0] + (r1 << g.blk[1])*g.mult[1] + (r2 << g.blk[2])*g.mult[2];
+        }
 #pragma unroll 4
         for (unsigned i = lane; i < (1u << FFR_DIR_ROW_SHIFT); i += 32u)
         {
             const W v = t[i];
             if (v)
             {
-                b[i] += v;
+                u64 at = base + i;
+                if (blocked)
+                {
+                    const unsigned o0 = i & ((1u << g.blk[0]) - 1u);
+                    const unsigned o1 = (i >> g.blk[0]) & ((1u << g.blk[1]) - 1u);
+                    const unsigned o2 = i >> (g.blk[0] + g.blk[1]);
+                    at = base + o0*g.mult[0] + o1*g.mult[1] + o2*g.mult[2];
+                }
+                buffer[at] += v;
                 t[i] = 0;
             }
         }
