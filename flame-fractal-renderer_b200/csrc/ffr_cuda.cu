@@ -656,6 +656,26 @@ bool jit_prepare(ffr_ctx *ctx, bool cache_only = false)
                     ok = ctx->sizes[d] % (1u << shape[ctx->dims][d]) == 0 && ctx->sizes[d] < (1ULL << 31);
                 for (uint32_t d = 0; d < 3; ++d)
                     cfg.dir_blk[d] = ok ? shape[ctx->dims][d] : 0u;
+                /* Directory cache in shared memory: ONE block of 768 chains per SM instead of three of
+                   256 (same 24 warps, same ISAAC footprint), which leaves ~35 KB for a 2-way cache of
+                   tag|slot words. Needs slots < 0xffff and rows < 0xffff sets-blocks (both hold for
+                   every buffer up to 128 GiB). FFR_DIR_CACHE=0: off. */
+                if (env_int("FFR_DIR_CACHE",1) != 0 && !getenv("FFR_JIT_TPB") && !getenv("FFR_JIT_MINB") &&
+                        cfg.dir_cap < 0xffffu)
+                {
+                    const size_t isaac = (size_t)32*768*ctx->elem;
+                    const size_t room = (size_t)227*1024 - 2048;
+                    unsigned sets = 0;
+                    if (isaac + 1024 < room)
+                        for (sets = 8192; sets >= 512 && isaac + 1024 + (size_t)sets*8 > room; sets >>= 1) {}
+                    if (sets >= 512 && (ctx->cells >> FFR_DIR_ROW_SHIFT) < (u64)0xffffu*sets)
+                    {
+                        cfg.dir_cache_sets = sets;
+                        cfg.tpb = 768;
+                        cfg.minb = 1;
+                        cfg.ns = cfg.cap = cfg.tpb;
+                    }
+                }
             }
         }
         std::string why;
@@ -665,7 +685,8 @@ bool jit_prepare(ffr_ctx *ctx, bool cache_only = false)
         if (!ctx->jit_source.empty())
         {
             /* randmem + randrsl columns, then the coefficient table [pair][xform] */
-            ctx->jit_smem = (size_t)32*cfg.tpb*ctx->elem + (size_t)cfg.npair*ctx->num_xforms*2*ctx->elem;
+            ctx->jit_smem = (size_t)32*cfg.tpb*ctx->elem + (size_t)cfg.npair*ctx->num_xforms*2*ctx->elem +
+                (size_t)cfg.dir_cache_sets*8;
             long spills = 0;
             double secs = 0.0;
             if (!jit::compile(ctx->jit_source,ctx->jit_cubin,ctx->jit_err,&secs,&ctx->jit_cached,&spills,cache_only))
@@ -679,7 +700,8 @@ bool jit_prepare(ffr_ctx *ctx, bool cache_only = false)
                 (cfg.dir_cap ? "compact tile of " + std::to_string(cfg.dir_cap) + " rows" +
                     ((cfg.dir_blk[0] | cfg.dir_blk[1] | cfg.dir_blk[2]) ? " (blocks of " + std::to_string(1u << cfg.dir_blk[0]) +
                         (ctx->dims > 1 ? "x" + std::to_string(1u << cfg.dir_blk[1]) : std::string()) +
-                        (ctx->dims > 2 ? "x" + std::to_string(1u << cfg.dir_blk[2]) : std::string()) + " cells)" : std::string()) + ", "
+                        (ctx->dims > 2 ? "x" + std::to_string(1u << cfg.dir_blk[2]) : std::string()) + " cells)" : std::string()) +
+                    (cfg.dir_cache_sets ? " + directory cache of " + std::to_string(2*cfg.dir_cache_sets) + " entries in shared memory" : std::string()) + ", "
                   : std::string()) +
                 std::to_string(cfg.npair) + " table rows, tpb " +
                 std::to_string(cfg.tpb) + ": " + std::to_string(spills) + " spill bytes; ";

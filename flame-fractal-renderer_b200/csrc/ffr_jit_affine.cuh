@@ -179,6 +179,17 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
     W *rng_base = (W*)smem;                       /* randmem columns, 16 words per chain */
     W *rsl_base = rng_base + 16*JTPB;             /* randrsl columns (read by cold paths only) */
     JPAIR *tab = (JPAIR*)(rsl_base + 16*JTPB);    /* varying coefficients [pair][xform] */
+#ifdef JDC_SETS
+    /* shared-memory cache of the row directory, JDC_SETS sets of two entries (tag << 16 | slot,
+       0xffff: empty). ncu on sierpinski_3d@512^3: the per-lane directory loads were half of an
+       L1TEX that ran at 90 % (one tag lookup per lane, 44 % hits); a hit here costs one 8-byte
+       shared-memory load. Entries are immutable facts (a row keeps its slot for the context's
+       lifetime), so the cache needs no invalidation; a row and its (set, tag) determine each
+       other: set = (row ^ tag*K) mod JDC_SETS, tag = row >> JDC_SETBITS. */
+    uint2 *dcache = (uint2*)(tab + JNPAIR*JNX);
+    for (int i = threadIdx.x; i < (int)JDC_SETS; i += JTPB)
+        dcache[i] = make_uint2(0xffffffffu,0xffffffffu);
+#endif
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -371,9 +382,28 @@ __device__ __forceinline__ void jaf_render(const RenderParams &prm)
                             const unsigned row = (unsigned)(bi >> FFR_DIR_ROW_SHIFT);
                             const unsigned off = (unsigned)bi & ((1u << FFR_DIR_ROW_SHIFT) - 1u);
 #endif
+#ifdef JDC_SETS
+                            const unsigned tag = row >> JDC_SETBITS;
+                            const unsigned set = (row ^ (tag*0x9E5u)) & (JDC_SETS - 1u);
+                            const uint2 e = dcache[set];
+                            unsigned slot = FFR_DIR_EMPTY;
+                            if ((e.x >> 16) == tag && (e.x & 0xffffu) != 0xffffu)
+                                slot = e.x & 0xffffu;
+                            else if ((e.y >> 16) == tag && (e.y & 0xffffu) != 0xffffu)
+                                slot = e.y & 0xffffu;
+                            else
+                            {
+                                slot = __ldca(&prm.dir[row]);
+                                if (slot >= FFR_DIR_DIRECT)
+                                    slot = jaf_dir_slow(prm.dir,prm.dir_next,row);
+                                if (slot < FFR_DIR_DIRECT)      /* remember it; the way alternates with the iteration */
+                                    ((unsigned*)dcache)[2u*set + ((unsigned)it & 1u)] = (tag << 16) | slot;
+                            }
+#else
                             unsigned slot = __ldca(&prm.dir[row]);
                             if (slot >= FFR_DIR_DIRECT)
                                 slot = jaf_dir_slow(prm.dir,prm.dir_next,row);
+#endif
                             if (slot < FFR_DIR_DIRECT)
                                 cell = acc + (((u64)slot << FFR_DIR_ROW_SHIFT) | off);
                         }

@@ -49,6 +49,7 @@ struct Config
     unsigned acc_mul = 0;   /* K1e: scramble multiplier of the accumulation tile (0: scatter into the buffer) */
     unsigned acc_gran = 0;  /* K1e: log2 of the cells that stay together in the tile */
     unsigned dir_cap = 0;   /* K1e: rows of the compact tile (0: none); excludes acc_mul */
+    unsigned dir_cache_sets = 0;     /* K1e compact tile: sets (2 ways each) of the shared-memory directory cache */
     unsigned dir_blk[3] = {0,0,0};   /* K1e compact tile: log2 of a row's extent along each axis (sum 9: a row is
                                         a BLOCK of 512 cells, e.g. 8x8x8); all zero: 512 consecutive cells */
 };
@@ -684,6 +685,13 @@ std::string generate_affine(const std::vector<unsigned char> &blobv, const u64 *
               << ((unsigned long long)cfg.dir_cap << FFR_DIR_ROW_SHIFT) << "ULL\n";
         if (cfg.dir_cap && (cfg.dir_blk[0] | cfg.dir_blk[1] | cfg.dir_blk[2]))
             h << "#define JDIR_BLOCKED 1\n";
+        if (cfg.dir_cap && cfg.dir_cache_sets)
+        {
+            unsigned bits = 0;
+            while ((1u << bits) < cfg.dir_cache_sets)
+                ++bits;
+            h << "#define JDC_SETS " << cfg.dir_cache_sets << "u\n#define JDC_SETBITS " << bits << "\n";
+        }
         h << "\n";
         o << "/* XForm::applyIteration for every xform of the flame; tb = coefficient table + xform index */\n";
         if (p_nz)
