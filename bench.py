@@ -77,8 +77,9 @@ BOUND_NOTE = {
     "sierpinski_1024": "K1e, bound by the L2 atomic units (one RED sector per sample into the "
                        "cell-scrambled L2-resident tile); DRAM idle",
     "barnsley_2048": "K1e, bound by the L2 atomic units (cell-scrambled L2-resident tile); DRAM idle",
-    "sierpinski3d_512": "K1e + compact tile: L2 atomic units + one row-directory lookup per sample; "
-                        "the hot rows are L2-resident inside the 1 GiB buffer",
+    "sierpinski3d_512": "K1e + compact tile of 8x8x8-cell block rows behind a row directory with a "
+                        "shared-memory cache: L2 atomic units (the hot rows are L2-resident inside the "
+                        "1 GiB buffer) plus the per-sample directory lookup",
     "barnsley_8192": "K1e + compact tile, dense attractor: part of the rows overflow the tile and "
                      "scatter into the 512 MiB buffer directly",
 }
@@ -87,10 +88,12 @@ BOUND_NOTE = {
 # committed `ncu --set full` captures (profiles/README.md); traffic per launch = this x plotted.
 # A workload without a capture reports null.
 NCU_DRAM_BYTES_PER_PLOTTED = {
-    "csci6360_4096": ((0.4210e9 + 3.8049e9) / 500.0e6, "profiles/r1_k1d_csci4096_sincos.summary.txt"),
-    "tkoz_test3_4096": ((1.8337e9 + 6.6085e9) / 327.7e6, "profiles/r1_k1d_tkoz3_4096.summary.txt"),
-    "sierpinski3d_512": ((8.99e6 + 0.006e6) / 1862.3e6, "profiles/r1_k1e_sierp3d_512_compact_tile.summary.txt"),
-    "barnsley_2048": ((25.83e6 + 0.008e6) / 1862.3e6, "profiles/r1_k1e_barnsley2048.summary.txt"),
+    # (dram read + dram write) / plotted samples of the captured launch (plotted = RED sectors,
+    # / 4 for the r = 3 flame whose cell is one sector hit by four REDs)
+    "csci6360_4096": ((0.4416e9 + 3.9159e9) / 500.2e6, "profiles/r2_k1d_csci4096.summary.txt"),
+    "tkoz_test3_4096": ((3.3952e9 + 12.2317e9) / (2373.8e6 / 4), "profiles/r2_k1d_tkoz3_4096.summary.txt"),
+    "sierpinski3d_512": ((7.99e6 + 0.0) / 465.7e6, "profiles/r2_k1e_sierp3d_512_block_rows_dircache.summary.txt"),
+    "barnsley_2048": ((25.67e6 + 0.005e6) / 466.0e6, "profiles/r2_k1e_barnsley2048.summary.txt"),
 }
 
 
