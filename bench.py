@@ -451,7 +451,8 @@ class Bench:
             done = sum(r.fetch_stats()["s_iter"] for r, _ in pipe)
             assert done == samples_per_step * (e2e_steps + 3), (done, samples_per_step, e2e_steps)
             if cell == 1:
-                assert all(int(o[::4097].sum()) > 0 for _, o in pipe)
+                # counts only: each host buffer holds exactly the samples its last step plotted
+                assert all(0 < int(o.sum()) <= samples_per_step for _, o in pipe)
             for r in extra:
                 r.close()
             del extra_host, pipe
