@@ -304,3 +304,41 @@ def test_device_sin_cos_accuracy(ffr):
     assert np.abs(got[:, 0] - wc)[~bigc].max() <= 4e-12
     ws = np.sin(xs) - 1.0
     assert np.abs(got[:, 1] - ws).max() <= 4e-16 * 2
+
+
+def test_device_atan2_accuracy(ffr):
+    """Device atan2 (the out-of-line libdevice wrapper m_atan2 in ffr_device.cuh; a constant-bank
+    re-implementation was measured in round 2 and bought < 1 %, so it was not kept) against glibc
+    through the `polar` variation, which gives
+    (atan2(y,x)/pi, r - 1). Stated tolerance: <= 2 ULP of atan2 (libdevice documents 2 ULP) + the
+    0.5 ULP of the multiplication by 1/pi; exact special cases: +-0 and +-pi/pi at the origin's
+    four sign combinations, the axes, and NaN in -> NaN out."""
+    import json
+    ident = {"A": [[1, 0], [0, 1]], "b": [0, 0]}
+    text = json.dumps({"dimensions": 2, "size": [8, 8], "bounds": [[-1, 1], [-1, 1]],
+                       "xforms": [{"weight": 1, "variations": [{"name": "polar", "weight": 1.0}],
+                                   "pre_affine": ident}]})
+    rng = np.random.default_rng(11)
+    n = 60000
+    x = np.concatenate([rng.uniform(-4, 4, n), rng.uniform(-1e-6, 1e-6, n), rng.uniform(-1e12, 1e12, n),
+                        rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-140, 140, n)])
+    y = np.concatenate([rng.uniform(-4, 4, n), rng.uniform(-4, 4, n), rng.uniform(-1e-3, 1e-3, n),
+                        rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-140, 140, n)])
+    sx = np.array([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 0.0, 0.0, 3.0, -3.0, 5e-324, -5e-324])
+    sy = np.array([0.0, 0.0, -0.0, -0.0, 0.0, 0.0, 1.0, -1.0, 3.0, 3.0, 5e-324, 5e-324])
+    x, y = np.concatenate([x, sx]), np.concatenate([y, sy])
+    pts = np.stack([x, y], axis=1)
+    r = ffr.BufferRenderer(ffr.Flame(text))
+    got = r.iterate_points(0, np.zeros(len(x), dtype=np.uint64), pts)
+    r.close()
+    want = np.arctan2(y, x)
+    wx = want * (1.0 / np.pi)                     # ox = P.ang * M_1_PI
+    big = np.abs(wx) > 1e-300
+    assert (np.abs(got[big, 0] - wx[big]) / np.spacing(np.abs(wx[big]))).max() <= 3.0
+    assert np.array_equal(np.signbit(got[:, 0]), np.signbit(wx))
+    k = len(x) - len(sx)
+    assert np.array_equal(got[k:k + 8, 0], wx[k:k + 8])       # zeros, axes: exact
+    nan_in = np.array([[np.nan, 1.0], [1.0, np.nan]])
+    r = ffr.BufferRenderer(ffr.Flame(text))
+    assert np.isnan(r.iterate_points(0, np.zeros(2, dtype=np.uint64), nan_in)[:, 0]).all()
+    r.close()
