@@ -299,3 +299,20 @@ def test_cli_worker_failure_is_reported(ffr, examples, tmp_path):
     p = _run_cli(ffr, ["-f", str(flame), "-o", str(out), "-s", "1000000", "-b", "1000", "--seed", "1",
                        "--gpus", str(n + 1)])
     assert p.returncode == 1 and "device index out of range" in p.stderr and not out.exists()
+
+
+def test_torchrun_nccl_reduce_matches_one_gpu(ffr):
+    """One process per GPU over NCCL (the bench's multi-GPU host): tests/nccl_reduce_worker.py on
+    two ranks; counts bit-identical to one GPU, colour sums to rounding, for a counts-only buffer
+    (one NCCL reduce) and for buffers with colour sums (all-to-all + K2d typed slice sum + sends)."""
+    import os
+    import subprocess
+    import sys
+    if ffr.lib().ffr_cuda_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577",
+                        os.path.join(here, "nccl_reduce_worker.py")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    assert p.stdout.count(": OK") == 3, p.stdout
