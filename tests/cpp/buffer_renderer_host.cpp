@@ -11,6 +11,7 @@ usage: buffer_renderer_host --construct FLAME.json      (constructor only; print
 */
 #include <ffr_buffer_renderer.hpp>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -35,6 +36,16 @@ static std::string quote(const std::string &s)
         o += (c == '\n') ? ' ' : c;
     }
     return o + "\"";
+}
+
+/* a double as JSON (Python's json reads Infinity / -Infinity: the extremes before the first sample) */
+static std::string number(double v)
+{
+    if (std::isinf(v))
+        return v > 0 ? "Infinity" : "-Infinity";
+    char num[40];
+    snprintf(num,sizeof num,"%.17g",v);
+    return num;
 }
 
 template <typename F> static std::string thrown(F f)
@@ -99,19 +110,12 @@ static int run(const std::string &json, int argc, char **argv)
     for (size_t i = 0; i < renderer.getXFormDistribution().size(); ++i)
         std::cout << (i ? ", " : "") << renderer.getXFormDistribution()[i];
     std::cout << "], \"extremes\": [";
-    char num[64];
     for (size_t d = 0; d < dims; ++d)
-    {
-        snprintf(num,sizeof num,"%s[%.17g, %.17g]",d ? ", " : "",renderer.getPointExtremes()[d].first,
-            renderer.getPointExtremes()[d].second);
-        std::cout << num;
-    }
+        std::cout << (d ? ", " : "") << "[" << number(renderer.getPointExtremes()[d].first) << ", "
+            << number(renderer.getPointExtremes()[d].second) << "]";
     std::cout << "], \"mult_d\": [";
     for (size_t d = 0; d < dims; ++d)
-    {
-        snprintf(num,sizeof num,"%s%.17g",d ? ", " : "",renderer.getDimMults()[d]);
-        std::cout << num;
-    }
+        std::cout << (d ? ", " : "") << number(renderer.getDimMults()[d]);
     std::cout << "], \"mult_i\": [";
     for (size_t d = 0; d < dims; ++d)
         std::cout << (d ? ", " : "") << renderer.getIndexMults()[d];

@@ -3,7 +3,7 @@
 # an ncu pass over the scatter-ceiling microbenchmarks (L2 RED sector counts, DRAM bytes)
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-( time timeout 1200 python -m pytest tests -m gpu -q -x ) > gpurun_out/r2z_pytest.log 2>&1
+( time timeout 1200 python -m pytest tests -m gpu -q ) > gpurun_out/r2z_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2z_pytest.log
 tail -6 gpurun_out/r2z_pytest.log | cut -c1-200
 ( timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" ) > gpurun_out/r2z_smoke.log 2>&1
