@@ -42,8 +42,6 @@ struct Config
     int ns = 512;           /* chain slots per block */
     int cap = 512;          /* K1d: ring capacity, power of two >= ns */
     int minb = 2;           /* blocks per SM asked of ptxas (register cap) */
-    bool abc_global = false; /* K1d: randa, randb, randc in the L2 scratch instead of shared memory */
-    bool stats_smem = true;  /* K1d: samples plotted and extremes per warp in shared memory */
     bool inline_math = false;
     bool async = true;      /* K1d (ffr_jit_async.cuh, queue scheduled) instead of K1c (lock step) */
     bool affine = false;    /* K1e (ffr_jit_affine.cuh): pure-affine flame, one chain per thread */
@@ -317,8 +315,6 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
        round-1 form (volatile accesses, no MEMBAR.CTA) for A/B measurements */
     if (cfg.async && getenv("FFR_JIT_ACQREL") && *getenv("FFR_JIT_ACQREL") == '0')
         h << "#define JQ_ACQREL 0\n";
-    if (cfg.async)
-        h << "#define JABC_GLOBAL " << (cfg.abc_global ? 1 : 0) << "\n#define JSTATS_SMEM " << (cfg.stats_smem ? 1 : 0) << "\n";
     if (cfg.async)
         h << "#define JRSL_SMEM " << (fl->uses_rng ? 1 : 0) << "\n"
           << (fl->uses_rng ? "" : "#define FFR_RSL_LOAD(p) __ldcg(p)\n");
