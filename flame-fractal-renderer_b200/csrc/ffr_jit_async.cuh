@@ -202,7 +202,7 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint2 s_ht[JNQ];         /* per queue: .x = head (claimed), .y = tail (reserved) */
     __shared__ int s_live;
-    __shared__ unsigned long long s_wxf[(JTPB/32)*JNX];   /* per warp: iterations executed per xform */
+    __shared__ unsigned long long s_wxf[(JTPB/32)*JNX];   /* per warp: iterations executed per xform (filled at the end) */
     W *rng_base = (W*)smem;                          /* randmem columns, 16 words per slot */
     W *st_a = rng_base + 16*JNS;                     /* randa, randb, randc, randcnt per slot */
     W *st_b = st_a + JNS;
@@ -234,6 +234,7 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
        ++s_iter and ++xf_dist[id] (:171-172) are counted once per popped chunk, below; s_iter is
        their sum. */
     u64 n_plot = 0;
+    u64 wcnt = 0;      /* lane q of a warp: iterations the warp executed of xform q (JNX <= 8 < 32) */
     T pmin[JD], pmax[JD];
 #pragma unroll
     for (int i = 0; i < JD; ++i)
@@ -248,11 +249,8 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
     {
         s_ht[tid] = make_uint2(0u,0u);
     }
-    for (int i = tid; i < (JTPB/32)*JNX; i += JTPB)
-        s_wxf[i] = 0ULL;
     const unsigned ht_s = (unsigned)__cvta_generic_to_shared(&s_ht[0]);
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
-    unsigned long long *my_wxf = s_wxf + (tid >> 5)*JNX;
     if (tid == 0)
         s_live = JNS;
     __syncthreads();
@@ -448,8 +446,8 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
             if (act)
                 it = s_it[slot];
             const unsigned cm = __ballot_sync(0xffffffffu,it >= 0);
-            if (lane == 0)
-                my_wxf[q] += (unsigned long long)__popc(cm);
+            if ((unsigned)lane == q)
+                wcnt += (unsigned long long)__popc(cm);   /* lane q counts xform q: one predicated add */
         }
         if (q == JQ_GEN)
         {
@@ -681,6 +679,8 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
             atomicMax(&prm.stats->pt_max[i],f64_to_ordered((double)pmax[i]));
         }
     }
+    if (lane < JNX)
+        s_wxf[(tid >> 5)*JNX + lane] = wcnt;
     __syncthreads();
     if (tid < JNX)
     {
