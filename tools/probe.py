@@ -30,7 +30,7 @@ def main():
     jits = [int(m) for m in os.environ.get("JIT", "1").split(",")]   # 1 off, 2 on
     for nm in names:
         ename, size = CONFIGS[nm]
-        fl = ffr.Flame(ex.example_json(ename, size=size))
+        fl = ffr.Flame(ex.example_json(ename, size=size), elem_size=int(os.environ.get("ELEM", "8")))
         for mode, rg, jit in [(m, g, j) for m in modes for g in regs for j in jits]:
             t0 = time.time()
             r = ffr.BufferRenderer(fl, scatter_mode=mode, blocks_per_sm=bps, regroup=rg, jit=jit)
