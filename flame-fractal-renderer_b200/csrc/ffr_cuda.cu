@@ -711,7 +711,10 @@ bool jit_prepare(ffr_ctx *ctx, bool cache_only = false)
         ctx->jit_note += why + "; ";
     }
     cfg.async = env_int("FFR_JIT_ASYNC",1) != 0;
-    cfg.tpb = env_int("FFR_JIT_TPB",cfg.async ? 320 : 256);
+    /* K1d: 320 threads x 2 blocks (96 registers) for the double build -- more warps there mean an
+       80-register cap, measured slower. The float build needs 72 registers and
+       has slots to spare: 448 threads measured +9 % over 320 (2.99e10 -> 3.25e10 on csci6360@4096^2) */
+    cfg.tpb = env_int("FFR_JIT_TPB",cfg.async ? (ctx->elem == 4 ? 448 : 320) : 256);
     cfg.minb = env_int("FFR_JIT_MINB",2);
     cfg.inline_math = env_int("FFR_JIT_INLINE_MATH",0) != 0;
     /* slots per block: as many as fit next to a second block in the 227 KB of an SM.
@@ -748,7 +751,7 @@ bool jit_prepare(ffr_ctx *ctx, bool cache_only = false)
     cfg.ns = ns;
     cfg.cap = pow2ceil(ns);
     ctx->jit_smem = smem_for(ns);
-    for (int attempt = 0; attempt < 2; ++attempt)
+    for (int attempt = 0; attempt < 3; ++attempt)
     {
         ctx->jit_source = ctx->elem == 8 ? jit::generate<double>(ctx->blob,ctx->colors,m0,m0_32,cfg)
                                          : jit::generate<float>(ctx->blob,ctx->colors,m0,m0_32,cfg);
@@ -764,9 +767,9 @@ bool jit_prepare(ffr_ctx *ctx, bool cache_only = false)
             "tpb " + std::to_string(cfg.tpb) + ": " + std::to_string(spills) + " spill bytes; ";
         /* 320 threads x 2 blocks cap the kernel at 96 registers; a flame whose xforms spill there
            runs faster with 256 threads (128 registers) than with spills through a thrashed L1 */
-        if (attempt == 0 && spills > 32 && cfg.tpb > 256 && !getenv("FFR_JIT_TPB"))
+        if (spills > 32 && cfg.tpb > 256 && !getenv("FFR_JIT_TPB"))
         {
-            cfg.tpb = 256;
+            cfg.tpb = cfg.tpb > 320 ? 320 : 256;
             continue;
         }
         break;
