@@ -214,7 +214,7 @@ void emit_xform(std::ostringstream &o, Pool<T> &pool, const std::string &name, i
         o << "    for (int i = 0; i < JD; ++i) t[i] = pin[i];\n";
     o << "    for (int i = 0; i < JD; ++i) v[i] = 0.0;\n";
     o << "    PolarT<T> P; P.r2 = P.r = P.ang = P.sa = P.ca = 0.0;\n";
-    if (D == 2)
+    if (D == 2 && xf.need != 0)
         o << "    JPOLAR(P," << xf.need << "u,t[0],t[1]);\n";
     for (uint32_t k = xf.var_begin; k < xf.var_begin + xf.var_count; ++k)
     {
@@ -234,7 +234,8 @@ void emit_xform(std::ostringstream &o, Pool<T> &pool, const std::string &name, i
             {
                 /* VariationFrom2D::calc_h, variations.hpp:94-105 */
                 o << "        const T a0 = t[" << var.axis_x << "], a1 = t[" << var.axis_y << "];\n";
-                o << "        JPOLAR(P," << var.need << "u,a0,a1);\n";
+                if (var.need != 0)
+                    o << "        JPOLAR(P," << var.need << "u,a0,a1);\n";
             }
             else
                 o << "        const T a0 = t[0], a1 = t[1];\n";
@@ -318,9 +319,35 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
     if (cfg.async)
         h << "#define JRSL_SMEM " << (fl->uses_rng ? 1 : 0) << "\n"
           << (fl->uses_rng ? "" : "#define FFR_RSL_LOAD(p) __ldcg(p)\n");
+    /* K1d, the out-of-line polar unit (r^2, r, atan2, y/r and x/r as the xform needs them): one
+       copy per need mask -- no mask tests, one reciprocal for both divisions, 54 instead of 75
+       instructions on the usual path -- when the flame uses at most two different masks; the
+       general copy otherwise. Measured: tkoz_test3 (masks 15, 7) +4 % with the specialised copies,
+       csci6360_project (15, 11, 3: three copies, 1.5 KB more hot code) -1.6 %.
+       FFR_JIT_POLAR_NEED=0/1 forces either form. */
+    bool polar_per_mask = false;
+    if (cfg.async)
+    {
+        std::vector<uint32_t> masks;
+        auto note = [&](uint32_t m) { if (m && std::find(masks.begin(),masks.end(),m) == masks.end()) masks.push_back(m); };
+        for (int k = 0; k < NX + (fl->has_final ? 1 : 0); ++k)
+        {
+            const DevXFormT<T> &xf = xfs[k];      /* the final xform is entry NX */
+            if (D == 2)
+                note(xf.need);
+            else
+                for (uint32_t q = xf.var_begin; q < xf.var_begin + xf.var_count; ++q)
+                    note(vars[q].need);
+        }
+        polar_per_mask = masks.size() <= 2;
+        if (const char *e = getenv("FFR_JIT_POLAR_NEED"))
+            polar_per_mask = *e != '0';
+    }
     if (cfg.async)
         h << ((getenv("FFR_JIT_SC_INLINE") && *getenv("FFR_JIT_SC_INLINE") == '1') ? "" : "#define FFR_SINCOS_OOL 1\n")
-          << "#define JPOLAR(P,need,x,y) P = polar_fill_ool<JT>(need,x,y)\n";
+          << (polar_per_mask
+                ? "#define JPOLAR(P,need,x,y) P = polar_fill_need<JT,need>(x,y)\n"
+                : "#define JPOLAR(P,need,x,y) P = polar_fill_ool<JT>(need,x,y)\n");
     else
         h << "#define JPOLAR(P,need,x,y) polar_fill(P,need,x,y)\n";
     h << "#include \"ffr_params.cuh\"\n";
