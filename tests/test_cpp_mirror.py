@@ -125,3 +125,29 @@ def test_two_calls_continue_the_chain_numbering_and_inputs_add(host_exe, ffr, po
     short.write_bytes(a.tobytes()[:-8])
     got = _run(host_exe, fpath, tmp_path / "c.buf", 0, batch, seed, inputs=[short])
     assert got["added"] is False and got["sum"] == 0      # short read: false, buffer untouched
+
+
+@pytest.mark.gpu
+def test_colour_buffer_layout_through_the_class(host_exe, ffr, po, examples, tmp_path):
+    """A flame with colour dimensions: cells x [count, c0, c1] (buffer_renderer.hpp:60-64), counts
+    bit for bit, colour sums to the order of the additions (the reference's multithreaded sums are
+    order dependent too): relative 1e-12."""
+    fl_json = json.loads(examples.example_json("sierpinski_triangle", size=[96, 64]))
+    fl_json["color_dimensions"] = 2
+    fl_json["color_speed"] = 0.25
+    for k, xf in enumerate(fl_json["xforms"]):
+        xf["color"] = [k / 2.0, 1.0 - k / 4.0]
+    text = json.dumps(fl_json)
+    fpath = tmp_path / "flame.json"
+    fpath.write_text(text)
+    out = tmp_path / "a.buf"
+    samples, batch, seed = 400_000, 2048, 11
+    got = _run(host_exe, fpath, out, samples, batch, seed)
+    fl = ffr.Flame(text)
+    want, st, _ = po.oracle_render_samples(fl, samples, batch, base_seed=seed)
+    cells = 96 * 64
+    assert (got["cells"], got["cell_size"], got["color_dims"]) == (cells, 3, 2)
+    a = np.fromfile(out, dtype=np.uint64).reshape(cells, 3)
+    w = want.reshape(cells, 3)
+    assert np.array_equal(a[:, 0], w[:, 0]) and got["sum"] == int(w[:, 0].sum()) == st["s_plot"]
+    assert np.allclose(a[:, 1:].copy().view(np.float64), w[:, 1:].copy().view(np.float64), rtol=1e-12, atol=0.0)
