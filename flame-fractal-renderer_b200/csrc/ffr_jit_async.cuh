@@ -191,6 +191,112 @@ __device__ __noinline__ unsigned long long jit_keys_from_rsl(const JW *rcol)
     return keys;
 }
 
+#ifndef JCOLD_START
+#define JCOLD_START 0
+#endif
+#ifndef JCOLD_IDLE
+#define JCOLD_IDLE 0
+#endif
+#ifndef JCOLD_BAD
+#define JCOLD_BAD 0
+#endif
+
+/* A slot takes a new chain: rng::setSeed((u64)seed_k), the first block of generator words, p =
+   randPoint (flame_rng.hpp:151-158). Once per chain; JCOLD_START compiles it out of line. */
+struct JitStart
+{
+    JW a, b, c;
+    unsigned long long keys;
+    JT p[JD];
+    int cnt;
+};
+
+__device__ __noinline__ JitStart jit_start_chain(JW *col, JW *rcol, u64 seed)
+{
+    RngT<JT> g;
+    g.col = col;
+    g.rcol = rcol;
+    g.seed_state(seed);
+    ++g.c;
+    const JitGenOut go = jit_gen_keys(g.col,g.rcol,g.a,(JW)(g.b + g.c));
+    g.a = go.a;
+    g.b = go.b;
+    g.cnt = 16;
+    JitStart st;
+#pragma unroll
+    for (int i = 0; i < JD; ++i)
+        st.p[i] = 2.0*g.num() - 1.0;
+    --g.cnt;        /* the first selection: word 15 - JD of the block */
+    st.a = g.a;
+    st.b = g.b;
+    st.c = g.c;
+    st.keys = go.keys;
+    st.cnt = g.cnt;
+    return st;
+}
+
+/* A bad value (buffer_renderer.hpp:175-186): count it, record the first FFR_MAX_BAD_RECORDED, and
+   say whether the limit is now exceeded (the launch then stops handing out chains). */
+__device__ __noinline__ bool jit_record_bad(DevStats *stats, u64 bv_limit, u64 json_id, Pt<JT,JD> p)
+{
+    const u64 idx = atomicAdd(&stats->n_bad,1ULL);
+    if (idx < FFR_MAX_BAD_RECORDED)
+    {
+        stats->bad_xf[idx] = json_id;
+#pragma unroll
+        for (int i = 0; i < JD; ++i)
+            stats->bad_pt[idx][i] = (double)p.v[i];
+    }
+    if (idx + 1 > bv_limit)
+    {
+        atomicOr((unsigned int*)&stats->abort,1u);
+        return true;
+    }
+    return false;
+}
+
+/* A warp found nothing to pop (converged, all 32 lanes; hd = the queue heads as the lanes read
+   them, lane < JNQ, else 0): live check, back-off, watchdog. stop: no live chain is left in the
+   block, or the watchdog fired. */
+struct JitIdle
+{
+    unsigned long long spins;
+    unsigned last_sig;
+    int stop;
+};
+
+__device__ __noinline__ JitIdle jit_idle(const int *live_p, unsigned hd, unsigned long long spins,
+        unsigned last_sig, unsigned int *abort_p)
+{
+    JitIdle r;
+    r.spins = spins;
+    r.last_sig = last_sig;
+    r.stop = 0;
+    int live = 0;
+    if ((threadIdx.x & 31) == 0)
+        live = *(volatile const int*)live_p;
+    live = __shfl_sync(0xffffffffu,live,0);
+    if (live == 0)
+    {
+        r.stop = 1;
+        return r;
+    }
+    __nanosleep(64);
+    const unsigned sig = __reduce_add_sync(0xffffffffu,hd);
+    if (sig != r.last_sig)
+    {
+        r.last_sig = sig;
+        r.spins = 0;
+    }
+    if (++r.spins > (1ULL << 24))
+    {
+        if ((threadIdx.x & 31) == 0)
+            atomicOr(abort_p,JABORT_WATCHDOG);
+        r.stop = 1;
+    }
+    return r;
+}
+
 /* MODES = false: plain RED scatter. MODES = true: prm.scatter_mode honoured (warp-aggregated,
    discard, trace), used by the scatter diagnostics and the attractor-replay roofline -- a second
    entry point, so that the render kernel proper carries neither the tests nor the code. */
@@ -258,6 +364,43 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
 #define LOAD_ABC(R,slot) do { (R).a = st_a[slot]; (R).b = st_b[slot]; (R).c = st_c[slot]; } while (0)
 #define STORE_ABC(R,slot) do { st_a[slot] = (R).a; st_b[slot] = (R).b; st_c[slot] = (R).c; } while (0)
 
+#if JCOLD_START
+#define JIT_CHAIN_START(slot,key,kk_) do { \
+        const JitStart st_ = jit_start_chain(rng_base + (slot),rsl_base + (slot), \
+            splitmix64(prm.base_seed + prm.chain_first + kk_)); \
+        _Pragma("unroll") \
+        for (int i_ = 0; i_ < JD; ++i_) \
+            sp[i_*JNS + (slot)] = st_.p[i_]; \
+        (key) = (unsigned)(st_.keys >> (4*st_.cnt)) & 15u; \
+        s_keys[slot] = st_.keys; \
+        st_a[slot] = st_.a; \
+        st_b[slot] = st_.b; \
+        st_c[slot] = st_.c; \
+        st_n[slot] = (W)st_.cnt; \
+    } while (0)
+#else
+#define JIT_CHAIN_START(slot,key,kk_) do { \
+        /* rng::setSeed((u64)seed_k), p = randPoint (flame_rng.hpp:151-158), first draw */ \
+        RngT<T> g_; \
+        g_.col = rng_base + (slot); \
+        g_.rcol = rsl_base + (slot); \
+        g_.seed_state(splitmix64(prm.base_seed + prm.chain_first + kk_)); \
+        ++g_.c; \
+        const JitGenOut go_ = jit_gen_keys(g_.col,g_.rcol,g_.a,(W)(g_.b + g_.c)); \
+        g_.a = go_.a; \
+        g_.b = go_.b; \
+        g_.cnt = 16; \
+        _Pragma("unroll") \
+        for (int i_ = 0; i_ < JD; ++i_) \
+            sp[i_*JNS + (slot)] = 2.0*g_.num() - 1.0; \
+        --g_.cnt;       /* the first selection: word 15 - JD of the block */ \
+        (key) = (unsigned)(go_.keys >> (4*g_.cnt)) & 15u; \
+        s_keys[slot] = go_.keys; \
+        STORE_ABC(g_,slot); \
+        st_n[slot] = (W)g_.cnt; \
+    } while (0)
+#endif
+
     /* Shared tail of every step: lanes flagged `fresh` take a new chain (or retire their slot),
        then every lane with a key queues its slot. Called by all 32 lanes, converged. */
 #define JIT_START_AND_PUSH(fresh,slot,key) do { \
@@ -275,24 +418,7 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
                                    : base_ + __popc(fm_ & ((1u << lane) - 1u)); \
                 if (kk_ < chain_count) \
                 { \
-                    /* rng::setSeed((u64)seed_k), p = randPoint (flame_rng.hpp:151-158), first draw */ \
-                    RngT<T> g_; \
-                    g_.col = rng_base + (slot); \
-                    g_.rcol = rsl_base + (slot); \
-                    g_.seed_state(splitmix64(prm.base_seed + prm.chain_first + kk_)); \
-                    ++g_.c; \
-                    const JitGenOut go_ = jit_gen_keys(g_.col,g_.rcol,g_.a,(W)(g_.b + g_.c)); \
-                    g_.a = go_.a; \
-                    g_.b = go_.b; \
-                    g_.cnt = 16; \
-                    _Pragma("unroll") \
-                    for (int i_ = 0; i_ < JD; ++i_) \
-                        sp[i_*JNS + (slot)] = 2.0*g_.num() - 1.0; \
-                    --g_.cnt;       /* the first selection: word 15 - JD of the block */ \
-                    (key) = (unsigned)(go_.keys >> (4*g_.cnt)) & 15u; \
-                    s_keys[slot] = go_.keys; \
-                    STORE_ABC(g_,slot); \
-                    st_n[slot] = (W)g_.cnt; \
+                    JIT_CHAIN_START(slot,key,kk_); \
                     s_it[slot] = -Real<T>::settle_iters; \
                     s_chain[slot] = kk_; \
                 } \
@@ -385,6 +511,17 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
                 }
                 continue;
             }
+#if JCOLD_IDLE
+            {
+                const JitIdle idle = jit_idle(&s_live,hd,spins,last_sig,(unsigned int*)&prm.stats->abort);
+                if (idle.stop)
+                    break;
+                spins = idle.spins;
+                last_sig = idle.last_sig;
+                ++fails;
+                continue;
+            }
+#endif
             int live = 0;
             if (lane == 0)
                 live = *(volatile int*)&s_live;
@@ -525,6 +662,13 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
                     bad |= bad_value(p[i]);
                 if (bad) /* :175-186 */
                 {
+#if JCOLD_BAD
+                    Pt<T,JD> pb;
+#pragma unroll
+                    for (int i = 0; i < JD; ++i)
+                        pb.v[i] = p[i];
+                    const bool over = jit_record_bad(prm.stats,prm.bv_limit,jit_json_id(k),pb);
+#else
                     u64 idx = atomicAdd(&prm.stats->n_bad,1ULL);
                     if (idx < FFR_MAX_BAD_RECORDED)
                     {
@@ -533,11 +677,12 @@ __device__ __forceinline__ void jit_render_async(const RenderParams &prm)
                         for (int i = 0; i < JD; ++i)
                             prm.stats->bad_pt[idx][i] = (double)p[i];
                     }
-                    if (idx + 1 > prm.bv_limit)
-                    {
+                    const bool over = idx + 1 > prm.bv_limit;
+                    if (over)
                         atomicOr((unsigned int*)&prm.stats->abort,1u);
+#endif
+                    if (over)
                         gone = true;
-                    }
                     else
                     {
                         /* iter.init() on the slot's own stream; pf, cf stay stale (Q3) */

@@ -310,8 +310,34 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
        contract, so only meaningful for flames that are compared statistically anyway */
     if (getenv("FFR_JIT_FMAD") && *getenv("FFR_JIT_FMAD") == '1')
         h << "/*FFR_NVRTC_FMAD*/\n";
-    if (cfg.async && !(getenv("FFR_JIT_GEN_ROLLED") && *getenv("FFR_JIT_GEN_ROLLED") == '0'))
-        h << "#define FFR_GEN_ROLLED 1\n";
+    if (cfg.async)
+    {
+        /* cold paths out of line: bit 0 chain start, 1 idle path, 2 bad-value record. Measured in all
+           eight combinations (csci6360_project / tkoz_test3 at 4096^2): only the bad-value record is
+           worth it (2.662e10 -> 2.671e10, 2.589e10 -> 2.601e10); chain start and idle path out of line
+           cost up to 8 % (their call sites keep more of the loop's state alive across a call) */
+        const char *c = getenv("FFR_JIT_COLD");
+        const int m = c ? atoi(c) : 4;
+        h << "#define JCOLD_START " << (m & 1) << "\n#define JCOLD_IDLE " << ((m >> 1) & 1) << "\n#define JCOLD_BAD " << ((m >> 2) & 1) << "\n";
+    }
+    if (cfg.async && !(getenv("FFR_JIT_SIN_VIA_SINCOS") && *getenv("FFR_JIT_SIN_VIA_SINCOS") == '0'))
+        h << "#define FFR_SIN_VIA_SINCOS 1\n";
+    /* K1d: gen() rolled to the four-step pattern of rngstep4 (a quarter of the unrolled code), or,
+       for flames whose xform bodies are large, to ONE step in the loop body (2 KB less hot code for
+       7 instructions more per iteration): csci6360_project (19 variations) 2.559e10 -> 2.658e10
+       with the one-step form, tkoz_test3 (14 variations) 2.583e10 -> 2.528e10. The threshold between
+       the two is the number of variations in the flame. FFR_JIT_GEN_ROLLED=0/1/2 forces a form. */
+    if (cfg.async)
+    {
+        uint32_t nvar = 0;
+        for (int k = 0; k < NX + (fl->has_final ? 1 : 0); ++k)
+            nvar += xfs[k].var_count;
+        int form = nvar >= 16 ? 2 : 1;
+        if (const char *e = getenv("FFR_JIT_GEN_ROLLED"))
+            form = atoi(e);
+        if (form)
+            h << "#define FFR_GEN_ROLLED " << form << "\n";
+    }
     /* K1d: queue entries as release stores / acquire loads (default); FFR_JIT_ACQREL=0 compiles the
        round-1 form (volatile accesses, no MEMBAR.CTA) for A/B measurements */
     if (cfg.async && getenv("FFR_JIT_ACQREL") && *getenv("FFR_JIT_ACQREL") == '0')
@@ -319,34 +345,30 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
     if (cfg.async)
         h << "#define JRSL_SMEM " << (fl->uses_rng ? 1 : 0) << "\n"
           << (fl->uses_rng ? "" : "#define FFR_RSL_LOAD(p) __ldcg(p)\n");
-    /* K1d, the out-of-line polar unit (r^2, r, atan2, y/r and x/r as the xform needs them): one
-       copy per need mask -- no mask tests, one reciprocal for both divisions, 54 instead of 75
-       instructions on the usual path -- when the flame uses at most two different masks; the
-       general copy otherwise. Measured: tkoz_test3 (masks 15, 7) +4 % with the specialised copies,
-       csci6360_project (15, 11, 3: three copies, 1.5 KB more hot code) -1.6 %.
-       FFR_JIT_POLAR_NEED=0/1 forces either form. */
-    bool polar_per_mask = false;
-    if (cfg.async)
-    {
-        std::vector<uint32_t> masks;
-        auto note = [&](uint32_t m) { if (m && std::find(masks.begin(),masks.end(),m) == masks.end()) masks.push_back(m); };
-        for (int k = 0; k < NX + (fl->has_final ? 1 : 0); ++k)
-        {
-            const DevXFormT<T> &xf = xfs[k];      /* the final xform is entry NX */
-            if (D == 2)
-                note(xf.need);
-            else
-                for (uint32_t q = xf.var_begin; q < xf.var_begin + xf.var_count; ++q)
-                    note(vars[q].need);
-        }
-        polar_per_mask = masks.size() <= 2;
-        if (const char *e = getenv("FFR_JIT_POLAR_NEED"))
-            polar_per_mask = *e != '0';
-    }
+    /* K1d, the out-of-line arithmetic units and the instruction cache. The hot code of a
+       variation flame is about as large as the 32 KB instruction cache, and what fits decides more
+       than the instruction count does (measured, csci6360_project / tkoz_test3 at 4096^2, samples/s):
+         general polar unit, separate sin / cos / sincos units      2.544e10 / 2.330e10
+         polar unit per need mask (54 instead of 75 instructions,
+           one reciprocal for both divisions; 1-3 copies)            2.503e10 / 2.426e10
+         sin and cos through the sincos unit (two units less)        2.490e10 / 2.338e10
+         both                                                        2.562e10 / 2.557e10
+       Both are the default; FFR_JIT_POLAR_NEED=0 / FFR_JIT_SIN_VIA_SINCOS=0 compile the other forms.
+       With atan2 called from the xform body instead of from inside the polar unit (copies shared
+       across NEED_ANG, a unit without calls): 2.511e10 / 2.583e10, and together with the one-step
+       gen() below 2.658e10 / 2.528e10. */
+    bool polar_per_mask = cfg.async;
+    if (const char *e = getenv("FFR_JIT_POLAR_NEED"))
+        polar_per_mask = cfg.async && *e != '0';
     if (cfg.async)
         h << ((getenv("FFR_JIT_SC_INLINE") && *getenv("FFR_JIT_SC_INLINE") == '1') ? "" : "#define FFR_SINCOS_OOL 1\n")
           << (polar_per_mask
-                ? "#define JPOLAR(P,need,x,y) P = polar_fill_need<JT,need>(x,y)\n"
+                ? ((getenv("FFR_JIT_POLAR_ANG") && *getenv("FFR_JIT_POLAR_ANG") == '0')
+                   ? "#define JPOLAR(P,need,x,y) P = polar_fill_need<JT,need>(x,y)\n"
+                   /* atan2 called from the xform body, not from inside the polar unit: masks that differ
+                      only in NEED_ANG share a copy, and the unit calls nothing on its usual path */
+                   : "#define JPOLAR(P,need,x,y) do { if (((need) & ~NEED_ANG) != 0u) P = polar_fill_need<JT,((need) & ~NEED_ANG)>(x,y); "
+                     "if ((need) & NEED_ANG) P.ang = m_atan2(y,x); } while (0)\n")
                 : "#define JPOLAR(P,need,x,y) P = polar_fill_ool<JT>(need,x,y)\n");
     else
         h << "#define JPOLAR(P,need,x,y) polar_fill(P,need,x,y)\n";
