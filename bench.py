@@ -69,11 +69,13 @@ UNIT = "samples/s"
 
 # What bounds each workload's render kernel (with the ncu evidence)
 BOUND_NOTE = {
-    "csci6360_4096": "K1d is instruction-issue / fp64-pipe bound (13 transcendental variations over 5 "
-                     "xforms); the scatter is hidden behind the arithmetic and HBM is < 5 % busy",
+    "csci6360_4096": "K1d is bound by its instruction stream (13 transcendental variations over 5 xforms: "
+                     "~1000 mostly dependent instructions per warp-iteration at 5 warps per scheduler, hot "
+                     "code as large as the instruction cache; fp64 pipe 37 % busy); the scatter is hidden "
+                     "behind the arithmetic and HBM is < 5 % busy",
     "csci6360_8192": "as csci6360_4096; the 512 MiB buffer no longer fits L2 but the scatter stays hidden",
-    "tkoz_test3_4096": "K1d, instruction-issue / fp64-pipe bound; 4 REDs per plotted sample (count + 3 "
-                       "colour sums, one 32-byte sector)",
+    "tkoz_test3_4096": "K1d, bound by its instruction stream like csci6360; 4 REDs per plotted sample "
+                       "(count + 3 colour sums, one 32-byte sector)",
     "sierpinski_1024": "K1e, bound by the L2 atomic units (one RED sector per sample into the "
                        "cell-scrambled L2-resident tile); DRAM idle",
     "barnsley_2048": "K1e, bound by the L2 atomic units (cell-scrambled L2-resident tile); DRAM idle",
