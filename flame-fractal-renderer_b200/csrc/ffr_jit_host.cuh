@@ -320,8 +320,6 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
         const int m = c ? atoi(c) : 4;
         h << "#define JCOLD_START " << (m & 1) << "\n#define JCOLD_IDLE " << ((m >> 1) & 1) << "\n#define JCOLD_BAD " << ((m >> 2) & 1) << "\n";
     }
-    if (cfg.async && getenv("FFR_JIT_SINCOS_FARCALL") && *getenv("FFR_JIT_SINCOS_FARCALL") == '1')
-        h << "#define FFR_SINCOS_FARCALL 1\n";
     if (cfg.async && !(getenv("FFR_JIT_SIN_VIA_SINCOS") && *getenv("FFR_JIT_SIN_VIA_SINCOS") == '0'))
         h << "#define FFR_SIN_VIA_SINCOS 1\n";
     /* K1d: gen() rolled to the four-step pattern of rngstep4 (a quarter of the unrolled code), or,
