@@ -332,7 +332,7 @@ std::string generate(const std::vector<unsigned char> &blobv, const std::vector<
         uint32_t nvar = 0;
         for (int k = 0; k < NX + (fl->has_final ? 1 : 0); ++k)
             nvar += xfs[k].var_count;
-        int form = nvar >= 16 ? 2 : 1;
+        int form = (nvar >= 16 && sizeof(T) == 8) ? 2 : 1;   /* the float build's code is small enough either way (3.53e10 vs 3.58e10 with the four-step form) */
         if (const char *e = getenv("FFR_JIT_GEN_ROLLED"))
             form = atoi(e);
         if (form)
