@@ -71,6 +71,30 @@ def main():
     print("== opcode mix ==")
     for k, v in ops.most_common(22):
         print("  %-10s %5.1f%% inst %5.1f%% samples" % (k, 100 * v / tot, 100 * osm[k] / ts))
+    # device functions follow the kernel body in address order (SASS-only page); each ends with a RET
+    srows = list(csv.reader(io.StringIO(run(["--page", "source", "--print-source", "sass", "--csv"]))))
+    shdr = next((r for r in srows if len(r) > 10 and r[0] == "Address"), None)
+    if shdr:
+        six = {h: i for i, h in enumerate(shdr)}
+        body = [r for r in srows if len(r) == len(shdr) and r[0] != "Address"]
+        def num(r, k):
+            try:
+                return float(r[six[k]])
+            except ValueError:
+                return 0.0
+        ti = sum(num(r, "Instructions Executed") for r in body) or 1
+        tsm = sum(num(r, "# Samples") for r in body) or 1
+        print("== code segments in address order (split after RET.REL.NODEC; the first is the kernel body) ==")
+        start = 0
+        for i, r in enumerate(body):
+            if "RET.REL.NODEC" in r[six["Source"]] or i == len(body) - 1:
+                blk = body[start:i + 1]
+                ie = sum(num(b, "Instructions Executed") for b in blk)
+                sm = sum(num(b, "# Samples") for b in blk)
+                if ie / ti > 0.002 or sm / tsm > 0.002:
+                    print("  instr %5d-%5d  %5.1f%% inst %5.1f%% smp | first: %s" % (
+                        start, i, 100 * ie / ti, 100 * sm / tsm, blk[0][six["Source"]].strip()[:48]))
+                start = i + 1
     print("== hot source lines ==")
     for a in sorted(lines, key=lambda x: -x[1])[:nlines]:
         print("  %5.2f%% inst %5.2f%% smp thr %4.1f | %s | %s" % (
