@@ -18,6 +18,12 @@ CONFIGS = {
     "barnsley1k": ("barnsley_fern", [1024, 1024]),
     "sierp4k": ("sierpinski_triangle", [4096, 4096]),
     "sierp3d256": ("sierpinski_triangle_3d", [256, 256, 256]),
+    "tkoz1": ("tkoz_test1", [4096, 4096]),
+    "tkoz2": ("tkoz_test2", [4096, 4096]),
+    "tkoz4": ("tkoz_test4", [4096, 4096]),
+    "tkoz5": ("tkoz_test5", [4096, 4096]),
+    "swv": ("sierpinski_with_variations", [4096, 4096]),
+    "flam3": ("flam3_test_1", [4096, 4096]),
 }
 
 def main():
