@@ -178,3 +178,33 @@ def test_queue_soak_many_launches_bit_exact(ffr, examples):
     for k in ("s_iter", "s_plot", "xf_dist", "n_bad", "pt_min", "pt_max"):
         assert s1[k] == s0[k], k
     assert np.array_equal(b1, b0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [17, 99])
+def test_polar_unit_shared_reciprocal_is_the_compilers_division(ffr, seed):
+    """K1d's polar unit computes y/r and x/r from ONE refined reciprocal (div_pair in
+    csrc/ffr_device.cuh: the compiler's own division sequence with the reciprocal shared, each
+    quotient falling back to the compiler's division when its acceptance test fails); the
+    ahead-of-time kernels divide plainly. On a flame of IEEE-only variations that read y/r and x/r
+    (hyperbolic: the only class-ii variation that does) every count
+    and statistic must therefore agree bit for bit -- one quotient rounded differently would send
+    its chain elsewhere. 2e10 samples by default (~4e10 divisions; FFR_DIV_SOAK_SAMPLES overrides)."""
+    import os
+    total = int(float(os.environ.get("FFR_DIV_SOAK_SAMPLES", "2e10")))
+    L = 4096
+    fl = ffr.Flame(flames.variation_flame("hyperbolic", size=[512, 512], color=False, final=True))
+    res = []
+    for jit in (ffr.JIT_ON, ffr.JIT_OFF):
+        r = ffr.BufferRenderer(fl, jit=jit)
+        if jit == ffr.JIT_ON:
+            assert "K1d queue-scheduled kernel" in r.jit_info["message"]
+            assert "polar_fill_need" in r.jit_source()
+        r.render_chains(0, total // L, L, base_seed=seed, bv_limit=1 << 60)
+        res.append((r.read_buffer(), r.stats))
+        r.close()
+    (b1, s1), (b0, s0) = res
+    assert s1["s_iter"] == (total // L) * L
+    for k in ("s_iter", "s_plot", "xf_dist", "n_bad", "pt_min", "pt_max"):
+        assert s1[k] == s0[k], k
+    assert np.array_equal(b1, b0)
