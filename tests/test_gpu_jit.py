@@ -199,7 +199,7 @@ def test_polar_unit_shared_reciprocal_is_the_compilers_division(ffr, seed):
         r = ffr.BufferRenderer(fl, jit=jit)
         if jit == ffr.JIT_ON:
             assert "K1d queue-scheduled kernel" in r.jit_info["message"]
-            assert "polar_fill_need" in r.jit_source()
+            assert "polar_fill_need" in r.jit_source
         r.render_chains(0, total // L, L, base_seed=seed, bv_limit=1 << 60)
         res.append((r.read_buffer(), r.stats))
         r.close()
